@@ -1,0 +1,258 @@
+/*
+ * nerfshop_b200.h — C ABI of the B200-native NeRFshop render path.
+ *
+ * This is the drop-in boundary for ONE hot path of graphdeco-inria/nerfshop:
+ *   Testbed::render_nerf            (reference src/testbed_nerf.cu:3066-3201)
+ *     -> NerfTracer::init_rays_from_camera (:2683-2756)
+ *     -> NerfTracer::trace                 (:2772-3002)
+ *     -> shade_kernel_nerf                 (:2448-2483)
+ * together with the three class surfaces it is called through:
+ *   NerfNetwork<T>   (include/neural-graphics-primitives/nerf_network.h:87-120)
+ *   EditOperator     (include/neural-graphics-primitives/editing/edit_operator.h:25-94)
+ *   Testbed::NerfTracer (include/neural-graphics-primitives/testbed.h:129-240)
+ *
+ * The reference has no FFI; its boundary is C++ classes. Every entry point
+ * below names the reference member it replaces. A C++ shim that keeps the
+ * reference's class names on top of this ABI is in nerfshop_b200/host/.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no exceptions cross the ABI; every call
+ *    returns an NsbStatus and nsb_last_error() gives the message.
+ *  - "host" pointers are read during the call and never retained.
+ *  - "dev" pointers are CUDA device pointers owned by the caller.
+ *  - matrices are column-major like Eigen (camera 3x4: 12 floats, col 0..3).
+ *  - one context per device; calls on one context are serialised by the caller
+ *    (same contract as the reference: everything runs on m_inference_stream).
+ */
+#ifndef NERFSHOP_B200_H
+#define NERFSHOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_ABI_VERSION 1
+
+/* reference: common_nerf.h:16-39 */
+#define NSB_NERF_GRIDSIZE 128u
+#define NSB_NERF_CASCADES 5u
+#define NSB_GRID_CELLS (NSB_NERF_CASCADES * NSB_NERF_GRIDSIZE * NSB_NERF_GRIDSIZE * NSB_NERF_GRIDSIZE)
+#define NSB_BITFIELD_BYTES (NSB_GRID_CELLS / 8u) /* 1,310,720 */
+
+typedef enum {
+	NSB_OK = 0,
+	NSB_ERR_INVALID = 1,     /* bad argument / unsupported configuration */
+	NSB_ERR_CUDA = 2,        /* a CUDA call failed (message has the CUDA error) */
+	NSB_ERR_STATE = 3,       /* call order: model / occupancy not uploaded yet */
+	NSB_ERR_UNSUPPORTED = 4  /* feature of the reference that this path does not cover */
+} NsbStatus;
+
+/* reference: common.h:71-84 (ERenderMode); only the modes that do not need
+ * network input gradients are covered. */
+typedef enum {
+	NSB_RENDER_AO = 0,
+	NSB_RENDER_SHADE = 1,
+	NSB_RENDER_POSITIONS = 3,
+	NSB_RENDER_DEPTH = 4,
+	NSB_RENDER_DISTANCE = 5,
+	NSB_RENDER_STEPSIZE = 6,
+	NSB_RENDER_COST = 8
+} NsbRenderMode;
+
+/* reference: common.h:107-112 (ENerfActivation) */
+typedef enum {
+	NSB_ACT_NONE = 0,
+	NSB_ACT_RELU = 1,
+	NSB_ACT_LOGISTIC = 2,
+	NSB_ACT_EXPONENTIAL = 3
+} NsbActivation;
+
+typedef struct NsbContext NsbContext;
+
+/* Network configuration = configs/nerf/base.json + the values Testbed::reset_network
+ * derives (testbed.cu:2258-2292). Only the base.json topology is implemented:
+ * HashGrid F=2 -> 64x1 density MLP (16 out) -> SH deg 4 -> 64x2 rgb MLP (3 out, padded 16). */
+typedef struct {
+	uint32_t n_levels;            /* 16 */
+	uint32_t n_features_per_level;/* 2  */
+	uint32_t log2_hashmap_size;   /* 19 */
+	uint32_t base_resolution;     /* 16 */
+	float    per_level_scale;     /* exp(ln(2048*aabb_scale/16)/15); fox: 1.5157166 */
+	uint32_t n_neurons;           /* 64 */
+	uint32_t n_hidden_density;    /* 1  */
+	uint32_t n_hidden_rgb;        /* 2  */
+	uint32_t sh_degree;           /* 4  */
+} NsbModelDesc;
+
+/* Per-frame inputs = the arguments of Testbed::render_nerf (testbed.h:305) plus the
+ * Testbed members it reads (testbed_nerf.cu:3082-3138). */
+typedef struct {
+	int32_t  width, height;            /* render_buffer.in_resolution() */
+	float    focal_length[2];          /* pixels */
+	float    screen_center[2];
+	float    camera0[12];              /* 3x4 column-major */
+	float    camera1[12];
+	float    rolling_shutter[4];
+	float    render_aabb_min[3], render_aabb_max[3]; /* m_render_aabb */
+	float    train_aabb_min[3],  train_aabb_max[3];  /* m_aabb */
+	float    cone_angle_constant;      /* m_nerf.cone_angle_constant */
+	float    min_transmittance;        /* m_nerf.rendering_min_transmittance (0.01) */
+	float    depth_scale;              /* 1 / dataset.scale */
+	int32_t  rgb_activation;           /* NsbActivation */
+	int32_t  density_activation;       /* NsbActivation */
+	int32_t  render_mode;              /* NsbRenderMode */
+	uint32_t spp_index;                /* render_buffer.spp() */
+	int32_t  snap_to_pixel_centers;
+	int32_t  apply_operators;          /* m_enable_edits && !m_distill */
+	int32_t  poisson_target;           /* NerfTracer::m_poisson_target */
+	int32_t  linear_colors;            /* m_nerf.training.linear_colors */
+	int32_t  min_mip;                  /* (show_accel>=0) ? show_accel : 0 */
+	/* image-plane partition (new; the reference is single-GPU): this context renders the
+	 * 16x8-pixel tiles whose linear index t satisfies t % tile_world == tile_rank. */
+	int32_t  tile_rank, tile_world;
+} NsbFrame;
+
+typedef enum { NSB_OP_CAGE = 0, NSB_OP_AFFINE = 1 } NsbEditOpType;
+
+/* Oriented box of affine_bounding_box.cuh:88-93 (only the fields contains() reads + center). */
+typedef struct {
+	float min[3], u[3], v[3], w[3], center[3];
+} NsbAffineBox;
+
+/* One EditOperator as the POD of its device-kernel arguments.
+ *  cage  : interpolate_tet (cage_deformation.cu:197-212) + compute_residual_poisson_kernel (:431-456)
+ *  affine: translate_in_box (affine_duplication.cu:92-102)
+ * All pointers are HOST pointers; nsb_set_edit_ops copies them to the device. */
+typedef struct {
+	int32_t type; /* NsbEditOpType */
+
+	/* ---- cage ---- */
+	int32_t copy;               /* GrowingSelection::m_copy */
+	int32_t apply_poisson;      /* CageDeformation::m_apply_poisson */
+	float   residual_amplitude; /* CageDeformation::m_residual_amplitude */
+	float   scene_aabb_min[3], scene_aabb_max[3];                 /* m_scene_aabb */
+	float   bbox_min[3], bbox_max[3];                             /* TetMesh::bbox (deformed, world) */
+	float   warped_bbox_min[3], warped_bbox_max[3];               /* TetMesh::warped_bbox */
+	float   original_warped_bbox_min[3], original_warped_bbox_max[3]; /* TetMesh::original_warped_bbox */
+	uint32_t n_tets, n_vertices, n_lut_idx;
+	const uint32_t* tet_lut_offsets;   /* [NSB_GRID_CELLS + 1] CSR offsets, cell = mip*128^3 + morton */
+	const uint32_t* tet_lut_idx;       /* [n_lut_idx] */
+	const uint32_t* tets;              /* [4*n_tets] */
+	const float*    vertices;          /* [3*n_vertices] deformed */
+	const float*    original_vertices; /* [3*n_vertices] canonical */
+	const float*    local_rotations;   /* [9*n_tets] column-major, or NULL */
+	const uint8_t*  original_bitfield; /* [NSB_BITFIELD_BYTES] */
+	const float*    boundary_shs;              /* [27*n_vertices] SH9RGB column-major (9 x 3), or NULL */
+	const float*    boundary_outside_density;  /* [n_vertices] or NULL */
+	const float*    boundary_residual_density; /* [n_vertices] or NULL */
+
+	/* ---- affine ---- */
+	NsbAffineBox selection_box;    /* m_warped_selection_box */
+	NsbAffineBox destination_box;  /* m_warped_destination_box */
+	float   translation[3];        /* m_warped_translation */
+	float   scale[3];              /* m_scale */
+	float   rotation[9];           /* m_rotation_matrix, column-major */
+	int32_t hide_original;         /* m_hide_original */
+	int32_t correct_dir;           /* m_correct_dir */
+} NsbEditOp;
+
+/* Counters of the last nsb_render call (the reference logs the same in ERenderMode::Cost,
+ * testbed_nerf.cu:3190-3200). */
+typedef struct {
+	uint64_t n_rays;          /* rays generated by this context (its tiles) */
+	uint64_t n_rays_alive;    /* rays that entered the render AABB */
+	uint64_t n_hit;           /* rays shaded into the framebuffer (A > 0.001) */
+	uint64_t n_samples;       /* network evaluations (occupied samples composited or masked) */
+	uint64_t n_old_samples;   /* extra density evaluations for the membrane target */
+	uint32_t n_kernel_launches;
+	float    gpu_ms;          /* device time of the render kernel(s), CUDA events */
+} NsbRenderStats;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+int         nsb_abi_version(void);
+const char* nsb_last_error(void);
+/* device < 0: current device. */
+NsbStatus   nsb_create(int device, NsbContext** out);
+NsbStatus   nsb_destroy(NsbContext* ctx);
+
+/* ---- state uploads (host pointers) ------------------------------------------------- */
+/* Number of fp16 parameters the description implies, in the reference's block order
+ * [density MLP][rgb MLP][hash grid] (nerf_network_full.h:316-349). */
+NsbStatus nsb_model_n_params(const NsbModelDesc* desc, uint64_t* n_params);
+/* replaces tcnn::Trainer::deserialize -> NerfNetwork::set_params (testbed.cu:3087). */
+NsbStatus nsb_upload_model(NsbContext* ctx, const NsbModelDesc* desc, const uint16_t* params_fp16, uint64_t n_params);
+/* replaces Testbed::Nerf::density_grid_bitfield (testbed.h:626; built at testbed.cu:3079). */
+NsbStatus nsb_upload_occupancy(NsbContext* ctx, const uint8_t* bitfield, uint64_t n_bytes);
+/* replaces NerfTracer::{add,delete,reset}_edit_operator; list order = m_edit_operators order
+ * (operators are applied in REVERSE list order, testbed_nerf.cu:2868,2899). n = 0 clears. */
+NsbStatus nsb_set_edit_ops(NsbContext* ctx, const NsbEditOp* ops, int32_t n);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* replaces Testbed::render_nerf. fb_dev: float4[width*height] (render_buffer.frame_buffer()),
+ * depth_dev: float[width*height] (depth_buffer()). Like the reference, pixels that hit are
+ * over-blended onto what fb_dev already holds; depth is set to 1e10 for every generated ray.
+ * Stream-ordered on `stream` (a cudaStream_t, may be NULL); returns without synchronising. */
+NsbStatus nsb_render(NsbContext* ctx, const NsbFrame* frame, float* fb_dev, float* depth_dev, void* stream);
+/* Same through HOST buffers (the reference's Testbed::render_to_cpu recipe, python_api.cu:129-175):
+ * clears a device framebuffer, renders, copies RGBA (+depth if non-NULL) back, synchronises. */
+NsbStatus nsb_render_host(NsbContext* ctx, const NsbFrame* frame, float* fb_host, float* depth_host);
+/* Synchronises and returns the counters of the last render. */
+NsbStatus nsb_get_stats(NsbContext* ctx, NsbRenderStats* out);
+
+/* Multi-GPU helpers: packed tile buffers for the single framebuffer gather.
+ * nsb_tiles_for_rank gives how many 16x8 tiles (and so how many float4 = n_tiles*128) a rank owns. */
+NsbStatus nsb_tiles_for_rank(int32_t width, int32_t height, int32_t rank, int32_t world, uint32_t* n_tiles);
+/* dst_packed[(local_tile*128 + lane)] <- fb[pixel(tile,lane)] for this rank's tiles. */
+NsbStatus nsb_pack_tiles(NsbContext* ctx, const float* fb_dev, const float* depth_dev, int32_t width, int32_t height,
+                         int32_t rank, int32_t world, float* dst_packed_rgba_dev, float* dst_packed_depth_dev, void* stream);
+/* inverse: scatter one rank's packed tiles into a full framebuffer. */
+NsbStatus nsb_unpack_tiles(NsbContext* ctx, const float* src_packed_rgba_dev, const float* src_packed_depth_dev,
+                           int32_t width, int32_t height, int32_t rank, int32_t world,
+                           float* fb_dev, float* depth_dev, void* stream);
+
+/* ---- operator-level entry points (unit parity; same device code as nsb_render) ------- */
+/* replaces NerfNetwork::inference_mixed_precision (testbed_nerf.cu:2892,2913):
+ * coords_dev: n x 7 floats {pos3 (warped), dt, dir3 (warped)} = NerfCoordinate (nerf.h:73);
+ * out_dev: fp16, row-major 16 x n_padded (element (k,i) at k*n_padded + i), rows 0-2 rgb raw, row 3 density raw.
+ * n_padded = n rounded up to 128 (tcnn::batch_size_granularity). */
+NsbStatus nsb_inference(NsbContext* ctx, const float* coords_dev, uint32_t n, uint16_t* out_dev, uint32_t n_padded, void* stream);
+/* replaces NerfNetwork::density (nerf_network_full.h:223-239): out_dev fp16 [16 x n_padded] row-major = density MLP output. */
+NsbStatus nsb_density(NsbContext* ctx, const float* coords_dev, uint32_t n, uint16_t* out_dev, uint32_t n_padded, void* stream);
+/* hash-grid encoding alone (tcnn GridEncoding inference): out_dev fp16 [32 x n_padded] row-major. */
+NsbStatus nsb_encode(NsbContext* ctx, const float* coords_dev, uint32_t n, uint16_t* out_dev, uint32_t n_padded, void* stream);
+/* replaces the loop over EditOperator::map_rays (testbed_nerf.cu:2896-2904): applies all uploaded
+ * operators in reverse order, in place; empty_mask_dev: n bytes (cleared first, like :2898). */
+NsbStatus nsb_map_rays(NsbContext* ctx, float* coords_dev, uint8_t* empty_mask_dev, uint32_t n, void* stream);
+/* replaces the loop over EditOperator::compute_poisson_full_residuals (:2867-2883) for a flat list of
+ * n samples: sh_dev [27*n], out_density_dev [n], residual_density_dev [n] (cleared first, like :2863-2866). */
+NsbStatus nsb_poisson_residuals(NsbContext* ctx, const float* coords_dev, uint32_t n,
+                                float* sh_dev, float* out_density_dev, float* residual_density_dev, void* stream);
+/* Occupancy march alone (init_rays + advance_pos + generate_next loop with no termination):
+ * for each listed pixel writes up to max_samples {t, dt, pos3, mip, cell_idx} records and the count.
+ * rec_dev: float[n_pixels*max_samples*5] (t,dt,x,y,z), idx_dev: uint32[n_pixels*max_samples*2] (mip, cell),
+ * count_dev: uint32[n_pixels] (total occupied samples on the ray, may exceed max_samples). */
+NsbStatus nsb_march_trace(NsbContext* ctx, const NsbFrame* frame, const uint32_t* pixels_dev, uint32_t n_pixels,
+                          uint32_t max_samples, float* rec_dev, uint32_t* idx_dev, uint32_t* count_dev, void* stream);
+
+/* ---- host-side geometry (the per-edit level; reference runs these on the CPU too) -------- */
+/* replaces TetMesh::build_tet_grid (tet_mesh.cu:369-667): CSR tet lookup over 5x128^3 cells for the
+ * given vertex set. offsets: [NSB_GRID_CELLS+1]; idx: caller buffer of capacity idx_capacity; *n_idx = needed.
+ * bitfield (may be NULL): [NSB_BITFIELD_BYTES], set where a tet touches the cell. */
+NsbStatus nsb_build_tet_grid(const float* vertices, uint32_t n_vertices, const uint32_t* tets, uint32_t n_tets,
+                             uint32_t* offsets, uint32_t* idx, uint64_t idx_capacity, uint64_t* n_idx, uint8_t* bitfield);
+/* replaces Cage::compute_mvc (cage.cu:7-36, mvc.h:126-188): weights [n_points x n_cage_vertices]. */
+NsbStatus nsb_compute_mvc(const float* cage_vertices, uint32_t n_cage_vertices, const uint32_t* cage_triangles, uint32_t n_triangles,
+                          const float* points, uint32_t n_points, float gamma, float* weights);
+/* replaces Cage::interpolate_with_mvc (cage.cu:39-55). */
+NsbStatus nsb_interpolate_with_mvc(const float* weights, uint32_t n_points, uint32_t n_cage_vertices,
+                                   const float* cage_vertices, float* points_out);
+/* replaces TetMesh::update_local_rotations (tet_mesh.cu:38-74): rotations [9*n_tets] column-major. */
+NsbStatus nsb_local_rotations(const float* vertices, const float* original_vertices, const uint32_t* tets, uint32_t n_tets, float* rotations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFSHOP_B200_H */

@@ -1,0 +1,873 @@
+// nsb_kernels.cu — kernels of the B200-native NeRFshop render path and the C ABI on top of them.
+//
+// The product kernel is k_render_fused: ONE persistent launch per frame that replaces the reference's
+// per-round pipeline (compact -> generate inputs -> [residuals] -> inference -> [map_rays] -> inference ->
+// composite, >= 12 launches + 3 host syncs per round, testbed_nerf.cu:2812-2990) and its 4.6 GB of
+// scratch: ray state lives in registers, samples go march -> deform -> hash encode -> tcgen05 MLP ->
+// composite without touching HBM, and finished rays are shaded straight into the framebuffer.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nerfshop_b200.h"
+#include "nsb_device.cuh"
+#include "nsb_tc.cuh"
+
+using namespace nsb;
+
+// =====================================================================================================
+// fused persistent renderer
+// =====================================================================================================
+struct RenderSmem {
+	tc::TileSmem tile;
+	uint32_t cur_tile;  // linear 16x8 tile index this CTA is currently handing out pixels from
+	uint32_t taken;     // pixels of cur_tile handed out so far (>= 128: exhausted)
+	uint32_t no_more;   // the global tile queue is empty
+	uint32_t pad;
+};
+
+enum { ST_RAYS = 0, ST_ALIVE = 1, ST_HIT = 2, ST_SAMPLES = 3, ST_OLD = 4, ST_N = 5 };
+
+// tile slot -> pixel: the four warps of a CTA each cover an 8x4 block so that the 32 lanes of a warp stay
+// spatially compact (coherent hash-grid and occupancy lookups)
+__device__ __forceinline__ bool tile_pixel(const DevFrame& f, uint32_t tile, uint32_t slot, uint32_t& px, uint32_t& py) {
+	uint32_t tx = tile % (uint32_t)f.tiles_x, ty = tile / (uint32_t)f.tiles_x;
+	uint32_t b = slot >> 5, l = slot & 31u;
+	px = tx * TILE_W + (b & 1u) * 8u + (l & 7u);
+	py = ty * TILE_H + (b >> 1) * 4u + (l >> 3);
+	return px < (uint32_t)f.W && py < (uint32_t)f.H;
+}
+
+// grid features of one sample -> this thread's row of the A operand (4 chunks x 8 fp16)
+__device__ __forceinline__ void encode_to_a32(tc::TileSmem& s, const DevModel& m, bool valid, V3 pw, uint32_t row) {
+#pragma unroll
+	for (int c = 0; c < 4; ++c) {
+		uint32_t h[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			__half2 v = __floats2half2_rn(0.0f, 0.0f);
+			if (valid) v = encode_level(m.levels[4 * c + j], m.grid, pw.x, pw.y, pw.z);
+			h[j] = tc::pack_h2(v);
+		}
+		tc::store_chunk(s.a32, c, row, make_uint4(h[0], h[1], h[2], h[3]));
+	}
+}
+
+__device__ __forceinline__ float h_lo(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed & 0xffffu))); }
+__device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed >> 16))); }
+
+__global__ void __launch_bounds__(128) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
+                                                      const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
+                                                      float4* __restrict__ fb, float* __restrict__ depth_out, uint32_t* tile_counter,
+                                                      unsigned long long* __restrict__ stats) {
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	RenderSmem& S = *reinterpret_cast<RenderSmem*>(smem_raw);
+	const uint32_t tid = threadIdx.x;
+	const uint32_t n_tiles = (uint32_t)(f.tiles_x * f.tiles_y);
+
+	const uint32_t tmem_base = tc::tile_setup(S.tile, m.w_image);
+	if (tid == 0) {
+		uint32_t t = atomicAdd(tile_counter, 1u);
+		uint32_t tile = (uint32_t)f.tile_rank + t * (uint32_t)f.tile_world;
+		S.cur_tile = tile;
+		S.no_more = tile >= n_tiles ? 1u : 0u;
+		S.taken = tile >= n_tiles ? (uint32_t)TILE_PIXELS : 0u;
+	}
+	__syncthreads();
+
+	const bool ops_on = f.apply_ops && n_ops > 0;
+	const float sat = 1.0f - f.min_T;  // rendering_min_transmittance test of composite_kernel_nerf :951
+	const V3 cam_fwd = v3(f.cam1[6], f.cam1[7], f.cam1[8]);
+	const V3 cam_org = v3(f.cam1[9], f.cam1[10], f.cam1[11]);
+
+	// ray state (registers)
+	bool alive = false;
+	V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), idir = v3(0, 0, 0);
+	float t = 0.0f;
+	float cr = 0, cg = 0, cb = 0, ca = 0, ray_depth = 0, max_weight = 0;
+	uint32_t pix = 0, n_steps = 0;
+	unsigned long long c_rays = 0, c_alive = 0, c_hit = 0, c_samples = 0, c_old = 0;
+	uint32_t phase = 0;
+
+	// shade_kernel_nerf (:2464-2482) for the ray this thread just finished (compact_kernel_nerf :2503 filter)
+	auto finish = [&](bool left_aabb) {
+		alive = false;
+		if (!(ca > 0.001f)) return;
+		++c_hit;
+		float r = cr, g = cg, b = cb, a = ca;
+		if (f.mode == NSB_RENDER_COST) {
+			float col = (float)(n_steps + (left_aabb ? 1u : 0u)) / 128.0f;
+			r = g = b = col;
+			a = 1.0f;
+		}
+		if (!f.linear_colors && f.mode == NSB_RENDER_SHADE) { r = srgb_to_linear(r); g = srgb_to_linear(g); b = srgb_to_linear(b); }
+		float4 prev = fb[pix];
+		float om = 1.0f - a;
+		fb[pix] = make_float4(__fmaf_rn(prev.x, om, r), __fmaf_rn(prev.y, om, g), __fmaf_rn(prev.z, om, b), __fmaf_rn(prev.w, om, a));
+		if (a > 0.2f) depth_out[pix] = ray_depth;
+	};
+
+	for (;;) {
+		if (tid == 0 && S.taken >= (uint32_t)TILE_PIXELS && !S.no_more) {
+			uint32_t tq = atomicAdd(tile_counter, 1u);
+			uint32_t tile = (uint32_t)f.tile_rank + tq * (uint32_t)f.tile_world;
+			if (tile >= n_tiles) {
+				S.no_more = 1u;
+			} else {
+				S.cur_tile = tile;
+				__threadfence_block();
+				S.taken = 0u;
+			}
+		}
+		const int any_alive = __syncthreads_or(alive ? 1 : 0);
+		if (!any_alive && *reinterpret_cast<volatile uint32_t*>(&S.no_more)) break;
+
+		// ---- acquire one occupied sample for this thread (refill the ray slot when it is free) ----
+		bool has_sample = false;
+		float dt = 0.0f;
+		V3 pos = v3(0, 0, 0);
+		for (;;) {
+			if (!alive) {
+				if (*reinterpret_cast<volatile uint32_t*>(&S.taken) >= (uint32_t)TILE_PIXELS) break;
+				uint32_t slot = atomicAdd(&S.taken, 1u);
+				if (slot >= (uint32_t)TILE_PIXELS) break;
+				uint32_t px, py;
+				if (!tile_pixel(f, *reinterpret_cast<volatile uint32_t*>(&S.cur_tile), slot, px, py)) continue;
+				pix = px + (uint32_t)f.W * py;
+				depth_out[pix] = 1e10f;  // :2581
+				++c_rays;
+				Ray r;
+				if (!make_ray(f, px, py, r)) continue;
+				++c_alive;
+				ro = r.o; rd = r.d;
+				idir = v3(div_(1.0f, rd.x), div_(1.0f, rd.y), div_(1.0f, rd.z));
+				t = fma_(ld_random_val(f.spp, pix * 786433u), calc_dt(r.t, f.cone), r.t);  // advance_pos_nerf :585
+				cr = cg = cb = ca = 0.0f;
+				ray_depth = 0.0f; max_weight = 0.0f; n_steps = 0;
+				alive = true;
+			}
+			if (n_steps >= MARCH_ITER - 1) { alive = false; continue; }  // still marching after MARCH_ITER steps: dropped (:2812)
+			uint32_t mip, cell;
+			if (!next_occupied(f, bitfield, ro, rd, idir, t, dt, pos, mip, cell)) { finish(true); continue; }
+			has_sample = true;
+			break;
+		}
+
+		// ---- network inputs: generate_next_nerf_network_inputs :690 ----
+		V3 pw = v3(0, 0, 0), dw = v3(0.5f, 0.5f, 0.5f);
+		float dtw = 0.0f;
+		bool empty = false;
+		Membrane mem;
+		mem.op = -1; mem.tet = -1; mem.dob = 0.0f; mem.drb = 0.0f;
+		bool need_old = false;
+		V3 pw_old = pw;
+		if (has_sample) {
+			pw = warp_position(pos, f.tmin, f.tmax);
+			dw = warp_direction(rd);
+			dtw = warp_dt(dt);
+			t = add(t, dt);
+			++n_steps;
+			++c_samples;
+			if (ops_on) {
+				if (any_poisson) {  // membrane residuals are evaluated in deformed space (:2867-2883)
+					poisson_one(ops, n_ops, pw, mem);
+					need_old = mem.dob > 1e-9f && f.poisson_target;
+				}
+				pw_old = pw;
+				map_one(ops, n_ops, pw, dw, empty);  // backward map into canonical space (:2896-2904)
+			}
+		}
+
+		// ---- "old" density: only read by the poisson-target blend (:773), so only evaluated there ----
+		float sigma_old_raw = 0.0f;
+		if (ops_on && any_poisson && f.poisson_target) {
+			if (__syncthreads_or(need_old ? 1 : 0)) {
+				uint32_t dens_old[8], dummy[8];
+				encode_to_a32(S.tile, m, need_old, pw_old, tid);
+				tc::run_network(S.tile, tmem_base, phase, nullptr, true, dens_old, dummy);
+				sigma_old_raw = h_lo(dens_old[0]);
+				if (need_old) ++c_old;
+			}
+		}
+
+		// ---- encode + fused MLPs ----
+		uint32_t dens[8], rgbo[8];
+		__half2 sh[8];
+		encode_to_a32(S.tile, m, has_sample, pw, tid);
+		encode_sh4(dw, sh);
+		tc::run_network(S.tile, tmem_base, phase, sh, false, dens, rgbo);
+
+		// ---- composite_kernel_nerf :750-955 for this one sample ----
+		if (has_sample) {
+			V3 cpos = unwarp_position(pw, f.tmin, f.tmax);
+			float T = 1.0f - ca;
+			float dtu = unwarp_dt(dtw);
+			float sigma = network_to_density(h_lo(dens[0]), f.density_act);  // row 3 = density MLP out[0] (extract_density)
+			float alpha;
+			const bool membrane = mem.dob > 1e-9f;
+			if (empty) {
+				alpha = 0.0f;
+			} else if (membrane) {
+				float val;
+				if (f.poisson_target) {
+					float target = network_to_density(sigma_old_raw, f.density_act);
+					val = fminf(fmaxf(target, sigma), sigma + mem.drb);
+				} else {
+					val = sigma + mem.drb;
+				}
+				alpha = 1.0f - __expf(-val * dtu);
+			} else {
+				alpha = 1.0f - __expf(-sigma * dtu);
+			}
+			float weight = alpha * T;
+			float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
+			if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
+			else if (f.mode == NSB_RENDER_POSITIONS) { rgb[0] = (cpos.x - 0.5f) / 2.0f + 0.5f; rgb[1] = (cpos.y - 0.5f) / 2.0f + 0.5f; rgb[2] = (cpos.z - 0.5f) / 2.0f + 0.5f; }
+			else if (f.mode == NSB_RENDER_DEPTH) { float z = dot3(cam_fwd, vsub(cpos, ro)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
+			else if (f.mode == NSB_RENDER_DISTANCE) { V3 q = vsub(cpos, ro); float z = sqrtf(dot3(q, q)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
+			else if (f.mode == NSB_RENDER_STEPSIZE) { float wdt = warp_dt(dtu); rgb[0] = rgb[1] = rgb[2] = wdt; }
+			if (membrane) {
+				float alpha_N = 1.0f - __expf(-sigma * dtu);
+				float alpha_R = 1.0f - __expf(-mem.dob * dtu);
+				float w_N = alpha_N / (alpha_N + alpha_R), w_R = alpha_R / (alpha_N + alpha_R);
+				float res[3];
+				membrane_rgb(ops, mem, unwarp_direction(dw), res);
+				cr = __fmaf_rn(weight, __fmaf_rn(w_R, res[0], w_N * rgb[0]), cr);
+				cg = __fmaf_rn(weight, __fmaf_rn(w_R, res[1], w_N * rgb[1]), cg);
+				cb = __fmaf_rn(weight, __fmaf_rn(w_R, res[2], w_N * rgb[2]), cb);
+			} else {
+				cr = __fmaf_rn(rgb[0], weight, cr);
+				cg = __fmaf_rn(rgb[1], weight, cg);
+				cb = __fmaf_rn(rgb[2], weight, cb);
+			}
+			ca += weight;
+			if (weight > max_weight) { max_weight = weight; ray_depth = dot3(cam_fwd, vsub(cpos, cam_org)); }
+			if (ca > sat) {
+				float a = ca;
+				cr = __fdiv_rn(cr, a); cg = __fdiv_rn(cg, a); cb = __fdiv_rn(cb, a); ca = __fdiv_rn(ca, a);
+				finish(false);
+			}
+		}
+	}
+
+	tc::tile_teardown(S.tile, tmem_base);
+
+	// counters: warp reduce, one atomic per warp
+	unsigned long long c[ST_N] = {c_rays, c_alive, c_hit, c_samples, c_old};
+#pragma unroll
+	for (int k = 0; k < ST_N; ++k) {
+		unsigned long long v = c[k];
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if ((tid & 31u) == 0 && v) atomicAdd(stats + k, v);
+	}
+}
+
+// =====================================================================================================
+// operator-level kernels (same device code as the fused renderer)
+// =====================================================================================================
+// NerfNetwork::inference_mixed_precision / ::density on a flat batch: one CTA = 128 samples.
+template <bool DENSITY_ONLY>
+__global__ void __launch_bounds__(128) k_inference(const DevModel m, const float* __restrict__ coords, uint32_t n, __half* __restrict__ out,
+                                                   uint32_t n_padded) {
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	tc::TileSmem& S = *reinterpret_cast<tc::TileSmem*>(smem_raw);
+	const uint32_t tid = threadIdx.x;
+	const uint32_t tmem_base = tc::tile_setup(S, m.w_image);
+	uint32_t phase = 0;
+	for (uint32_t base = blockIdx.x * 128u; base < n_padded; base += gridDim.x * 128u) {
+		uint32_t i = base + tid;
+		bool valid = i < n;
+		V3 pw = v3(0, 0, 0), dw = v3(0.5f, 0.5f, 0.5f);
+		if (valid) {
+			pw = v3(coords[7 * (size_t)i], coords[7 * (size_t)i + 1], coords[7 * (size_t)i + 2]);
+			dw = v3(coords[7 * (size_t)i + 4], coords[7 * (size_t)i + 5], coords[7 * (size_t)i + 6]);
+		}
+		uint32_t dens[8], rgbo[8];
+		__half2 sh[8];
+		encode_to_a32(S, m, valid, pw, tid);
+		encode_sh4(dw, sh);
+		tc::run_network(S, tmem_base, phase, sh, DENSITY_ONLY, dens, rgbo);
+		if (i < n_padded) {
+			const uint32_t* src = DENSITY_ONLY ? dens : rgbo;
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				out[(size_t)(2 * k) * n_padded + i] = __ushort_as_half((unsigned short)(src[k] & 0xffffu));
+				out[(size_t)(2 * k + 1) * n_padded + i] = __ushort_as_half((unsigned short)(src[k] >> 16));
+			}
+			if (!DENSITY_ONLY) out[(size_t)3 * n_padded + i] = __ushort_as_half((unsigned short)(dens[0] & 0xffffu));  // extract_density
+		}
+	}
+	tc::tile_teardown(S, tmem_base);
+}
+
+__global__ void k_encode(const DevModel m, const float* __restrict__ coords, uint32_t n, __half* __restrict__ out, uint32_t n_padded) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float x = coords[7 * (size_t)i], y = coords[7 * (size_t)i + 1], z = coords[7 * (size_t)i + 2];
+#pragma unroll 4
+	for (uint32_t l = 0; l < MAX_LEVELS; ++l) {
+		__half2 v = encode_level(m.levels[l], m.grid, x, y, z);
+		out[(size_t)(2 * l) * n_padded + i] = __low2half(v);
+		out[(size_t)(2 * l + 1) * n_padded + i] = __high2half(v);
+	}
+}
+
+__global__ void k_map_rays(const DevOp* __restrict__ ops, int n_ops, float* __restrict__ coords, uint8_t* __restrict__ empty_mask, uint32_t n) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	V3 pw = v3(coords[7 * (size_t)i], coords[7 * (size_t)i + 1], coords[7 * (size_t)i + 2]);
+	V3 dw = v3(coords[7 * (size_t)i + 4], coords[7 * (size_t)i + 5], coords[7 * (size_t)i + 6]);
+	bool empty = false;
+	map_one(ops, n_ops, pw, dw, empty);
+	coords[7 * (size_t)i] = pw.x; coords[7 * (size_t)i + 1] = pw.y; coords[7 * (size_t)i + 2] = pw.z;
+	coords[7 * (size_t)i + 4] = dw.x; coords[7 * (size_t)i + 5] = dw.y; coords[7 * (size_t)i + 6] = dw.z;
+	empty_mask[i] = empty ? 1 : 0;
+}
+
+__global__ void k_poisson(const DevOp* __restrict__ ops, int n_ops, const float* __restrict__ coords, uint32_t n, float* __restrict__ sh,
+                          float* __restrict__ od, float* __restrict__ rd) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	Membrane mem;
+	poisson_one(ops, n_ops, v3(coords[7 * (size_t)i], coords[7 * (size_t)i + 1], coords[7 * (size_t)i + 2]), mem);
+	od[i] = mem.dob;
+	rd[i] = mem.drb;
+	for (int k = 0; k < 27; ++k) sh[27 * (size_t)i + k] = mem.op >= 0 ? membrane_sh(ops, mem, k) : 0.0f;
+}
+
+__global__ void k_march_trace(const DevFrame f, const uint8_t* __restrict__ bitfield, const uint32_t* __restrict__ pixels, uint32_t n_pixels,
+                              uint32_t max_samples, float* __restrict__ rec, uint32_t* __restrict__ idx, uint32_t* __restrict__ count) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pixels) return;
+	uint32_t pix = pixels[i];
+	uint32_t px = pix % (uint32_t)f.W, py = pix / (uint32_t)f.W;
+	Ray r;
+	uint32_t c = 0;
+	if (make_ray(f, px, py, r)) {
+		V3 idir = v3(div_(1.0f, r.d.x), div_(1.0f, r.d.y), div_(1.0f, r.d.z));
+		float t = fma_(ld_random_val(f.spp, pix * 786433u), calc_dt(r.t, f.cone), r.t);
+		while (c < MARCH_ITER) {
+			float dt; V3 pos; uint32_t mip, cell;
+			if (!next_occupied(f, bitfield, r.o, r.d, idir, t, dt, pos, mip, cell)) break;
+			if (c < max_samples) {
+				float* rr = rec + ((size_t)i * max_samples + c) * 5;
+				rr[0] = t; rr[1] = dt; rr[2] = pos.x; rr[3] = pos.y; rr[4] = pos.z;
+				uint32_t* ii = idx + ((size_t)i * max_samples + c) * 2;
+				ii[0] = mip; ii[1] = cell;
+			}
+			++c;
+			t = add(t, dt);
+		}
+	}
+	count[i] = c;
+}
+
+// packed tile buffers for the single multi-GPU framebuffer gather
+__global__ void k_pack_tiles(const float4* __restrict__ fb, const float* __restrict__ depth, int W, int H, int tiles_x, int n_tiles, int rank, int world,
+                             float4* __restrict__ dst, float* __restrict__ dst_depth, int unpack) {
+	uint32_t local = blockIdx.x;
+	uint32_t tile = (uint32_t)rank + local * (uint32_t)world;
+	if (tile >= (uint32_t)n_tiles) return;
+	uint32_t lane = threadIdx.x;  // 0..127
+	uint32_t px = (tile % (uint32_t)tiles_x) * TILE_W + (lane % TILE_W), py = (tile / (uint32_t)tiles_x) * TILE_H + (lane / TILE_W);
+	if (px >= (uint32_t)W || py >= (uint32_t)H) return;
+	size_t p = (size_t)px + (size_t)W * py, q = (size_t)local * TILE_PIXELS + lane;
+	if (!unpack) {
+		dst[q] = fb[p];
+		if (dst_depth && depth) dst_depth[q] = depth[p];
+	} else {
+		const_cast<float4*>(fb)[p] = dst[q];
+		if (dst_depth && depth) const_cast<float*>(depth)[p] = dst_depth[q];
+	}
+}
+
+// =====================================================================================================
+// host side: context, uploads, C ABI
+// =====================================================================================================
+static thread_local std::string g_last_error;
+static NsbStatus fail(NsbStatus s, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	return s;
+}
+#define CU(call)                                                                                                 \
+	do {                                                                                                         \
+		cudaError_t e__ = (call);                                                                                \
+		if (e__ != cudaSuccess) return fail(NSB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+struct NsbContext {
+	int device = 0;
+	int sm_count = 0;
+	int ctas_per_sm = 1;
+	bool has_model = false, has_occ = false;
+	NsbModelDesc desc{};
+	DevModel model{};
+	__half2* d_grid = nullptr;
+	uint8_t* d_wimage = nullptr;
+	__half* d_wrow = nullptr;
+	uint8_t* d_bitfield = nullptr;
+	DevOp* d_ops = nullptr;
+	int n_ops = 0;
+	int any_poisson = 0;
+	std::vector<void*> op_allocs;
+	uint32_t* d_tile_counter = nullptr;
+	unsigned long long* d_stats = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool timed = false;
+	uint32_t launches = 0;
+	float* d_fb = nullptr;
+	float* d_depth = nullptr;
+	size_t fb_pixels = 0;
+	cudaStream_t stream = nullptr;
+};
+
+static uint32_t next_multiple_u32(uint32_t v, uint32_t m) { return ((v + m - 1) / m) * m; }
+
+static bool build_levels(const NsbModelDesc* d, DevLevel* L, uint64_t* n_grid_entries) {
+	if (!d || d->n_levels != 16 || d->n_features_per_level != 2 || d->n_neurons != 64 || d->n_hidden_density != 1 || d->n_hidden_rgb != 2 ||
+	    d->sh_degree != 4 || d->log2_hashmap_size == 0 || d->log2_hashmap_size > 24 || d->base_resolution == 0 || !(d->per_level_scale > 0.0f))
+		return false;
+	float l2s = log2f(d->per_level_scale);
+	uint64_t offset = 0;
+	for (uint32_t l = 0; l < d->n_levels; ++l) {
+		float scale = exp2f((float)l * l2s) * (float)d->base_resolution - 1.0f;  // tcnn grid_scale
+		uint32_t res = (uint32_t)ceilf(scale) + 1u;                                // tcnn grid_resolution
+		double dense = (double)res * res * res;
+		uint32_t max_params = 0xffffffffu / 2;
+		uint32_t n = dense > (double)max_params ? max_params : (uint32_t)dense;
+		n = next_multiple_u32(n, 8u);
+		n = n < (1u << d->log2_hashmap_size) ? n : (1u << d->log2_hashmap_size);
+		L[l].scale = scale;
+		L[l].res = res;
+		L[l].offset = (uint32_t)offset;
+		L[l].size = n;
+		L[l].hashed = dense > (double)n ? 1u : 0u;
+		L[l].res2 = L[l].hashed ? 0u : res * res;
+		L[l].mask = (n & (n - 1)) == 0 ? n - 1 : 0u;
+		L[l].pad = 0;
+		offset += n;
+	}
+	*n_grid_entries = offset;
+	return true;
+}
+static const uint64_t kMlpParams = 64 * 32 + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64;
+
+extern "C" int nsb_abi_version(void) { return NSB_ABI_VERSION; }
+extern "C" const char* nsb_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" NsbStatus nsb_model_n_params(const NsbModelDesc* desc, uint64_t* n_params) {
+	DevLevel L[MAX_LEVELS];
+	uint64_t n = 0;
+	if (!n_params || !build_levels(desc, L, &n)) return fail(NSB_ERR_INVALID, "unsupported model description (only the configs/nerf/base.json topology is implemented)");
+	*n_params = kMlpParams + 2 * n;
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
+	if (!out) return fail(NSB_ERR_INVALID, "out is null");
+	int n_dev = 0;
+	CU(cudaGetDeviceCount(&n_dev));
+	if (n_dev == 0) return fail(NSB_ERR_CUDA, "no CUDA device: nerfshop_b200 has no CPU fallback");
+	if (device < 0) CU(cudaGetDevice(&device));
+	if (device >= n_dev) return fail(NSB_ERR_INVALID, "device %d out of range (%d devices)", device, n_dev);
+	CU(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) return fail(NSB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+	NsbContext* c = new NsbContext();
+	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	CU(cudaMalloc(&c->d_tile_counter, sizeof(uint32_t)));
+	CU(cudaMalloc(&c->d_stats, ST_N * sizeof(unsigned long long)));
+	CU(cudaMemset(c->d_stats, 0, ST_N * sizeof(unsigned long long)));
+	CU(cudaEventCreate(&c->ev0));
+	CU(cudaEventCreate(&c->ev1));
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RenderSmem)));
+	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
+	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
+	int occ = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_fused, 128, sizeof(RenderSmem)));
+	// TMEM: 512 columns per SM, 64 per CTA
+	c->ctas_per_sm = occ < 1 ? 1 : (occ > 8 ? 8 : occ);
+	*out = c;
+	return NSB_OK;
+}
+
+static void free_ops(NsbContext* c) {
+	for (void* p : c->op_allocs) cudaFree(p);
+	c->op_allocs.clear();
+	if (c->d_ops) cudaFree(c->d_ops);
+	c->d_ops = nullptr;
+	c->n_ops = 0;
+	c->any_poisson = 0;
+}
+
+extern "C" NsbStatus nsb_destroy(NsbContext* c) {
+	if (!c) return NSB_OK;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	free_ops(c);
+	cudaFree(c->d_grid); cudaFree(c->d_wimage); cudaFree(c->d_wrow); cudaFree(c->d_bitfield);
+	cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_fb); cudaFree(c->d_depth);
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+	return NSB_OK;
+}
+
+// [N x K] row-major fp16 -> UMMA K-major no-swizzle operand image (nsb_tc.cuh header comment)
+static void to_operand_layout(const uint16_t* W, uint32_t N, uint32_t K, uint8_t* dst) {
+	for (uint32_t n = 0; n < N; ++n)
+		for (uint32_t k = 0; k < K; ++k) {
+			size_t off = (size_t)(k / 8) * (N * 16) + (size_t)n * 16 + (k % 8) * 2;
+			memcpy(dst + off, W + (size_t)n * K + k, 2);
+		}
+}
+
+extern "C" NsbStatus nsb_upload_model(NsbContext* c, const NsbModelDesc* desc, const uint16_t* params, uint64_t n_params) {
+	if (!c || !desc || !params) return fail(NSB_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(c->device));
+	DevModel m{};
+	uint64_t n_grid = 0;
+	if (!build_levels(desc, m.levels, &n_grid)) return fail(NSB_ERR_INVALID, "unsupported model description (only the configs/nerf/base.json topology is implemented)");
+	if (n_params != kMlpParams + 2 * n_grid) return fail(NSB_ERR_INVALID, "n_params %llu != expected %llu", (unsigned long long)n_params, (unsigned long long)(kMlpParams + 2 * n_grid));
+	CU(cudaDeviceSynchronize());
+	cudaFree(c->d_grid); cudaFree(c->d_wimage); cudaFree(c->d_wrow);
+	c->d_grid = nullptr; c->d_wimage = nullptr; c->d_wrow = nullptr;
+	// block order: density MLP, rgb MLP, hash grid (nerf_network_full.h:316-349)
+	std::vector<uint8_t> image(tc::W_BYTES);
+	const uint16_t* w = params;
+	to_operand_layout(w, 64, 32, image.data() + tc::W1_OFF); w += 64 * 32;
+	to_operand_layout(w, 16, 64, image.data() + tc::W2_OFF); w += 16 * 64;
+	to_operand_layout(w, 64, 32, image.data() + tc::W3_OFF); w += 64 * 32;
+	to_operand_layout(w, 64, 64, image.data() + tc::W4_OFF); w += 64 * 64;
+	to_operand_layout(w, 16, 64, image.data() + tc::W5_OFF); w += 16 * 64;
+	CU(cudaMalloc(&c->d_wimage, tc::W_BYTES));
+	CU(cudaMemcpy(c->d_wimage, image.data(), tc::W_BYTES, cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&c->d_wrow, kMlpParams * 2));
+	CU(cudaMemcpy(c->d_wrow, params, kMlpParams * 2, cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&c->d_grid, n_grid * 4));
+	CU(cudaMemcpy(c->d_grid, params + kMlpParams, n_grid * 4, cudaMemcpyHostToDevice));
+	m.grid = c->d_grid;
+	m.w_image = c->d_wimage;
+	m.w_rowmajor = c->d_wrow;
+	m.n_levels = desc->n_levels;
+	c->model = m;
+	c->desc = *desc;
+	c->has_model = true;
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_upload_occupancy(NsbContext* c, const uint8_t* bitfield, uint64_t n_bytes) {
+	if (!c || !bitfield) return fail(NSB_ERR_INVALID, "null argument");
+	if (n_bytes != NSB_BITFIELD_BYTES) return fail(NSB_ERR_INVALID, "bitfield must be %u bytes (5 x 128^3 / 8)", NSB_BITFIELD_BYTES);
+	CU(cudaSetDevice(c->device));
+	if (!c->d_bitfield) CU(cudaMalloc(&c->d_bitfield, NSB_BITFIELD_BYTES));
+	CU(cudaDeviceSynchronize());
+	CU(cudaMemcpy(c->d_bitfield, bitfield, NSB_BITFIELD_BYTES, cudaMemcpyHostToDevice));
+	c->has_occ = true;
+	return NSB_OK;
+}
+
+template <typename T>
+static NsbStatus dev_copy(NsbContext* c, const T* host, size_t count, const T** out) {
+	*out = nullptr;
+	if (!host || count == 0) return NSB_OK;
+	void* p = nullptr;
+	CU(cudaMalloc(&p, count * sizeof(T)));
+	c->op_allocs.push_back(p);
+	CU(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+	*out = reinterpret_cast<const T*>(p);
+	return NSB_OK;
+}
+static void cp3(float* d, const float* s) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+static void cpbox(DevAffineBox& d, const NsbAffineBox& s) { cp3(d.mn, s.min); cp3(d.u, s.u); cp3(d.v, s.v); cp3(d.w, s.w); cp3(d.c, s.center); }
+
+extern "C" NsbStatus nsb_set_edit_ops(NsbContext* c, const NsbEditOp* ops, int32_t n) {
+	if (!c || n < 0 || (n > 0 && !ops)) return fail(NSB_ERR_INVALID, "bad arguments");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	free_ops(c);
+	if (n == 0) return NSB_OK;
+	std::vector<DevOp> dev(n);
+	int any_poisson = 0;
+	for (int i = 0; i < n; ++i) {
+		const NsbEditOp& s = ops[i];
+		DevOp& d = dev[i];
+		memset(&d, 0, sizeof(d));
+		d.type = s.type;
+		if (s.type == NSB_OP_CAGE) {
+			d.copy = s.copy;
+			d.apply_poisson = s.apply_poisson;
+			d.amp = s.residual_amplitude;
+			cp3(d.amin, s.scene_aabb_min); cp3(d.amax, s.scene_aabb_max);
+			cp3(d.bmin, s.bbox_min); cp3(d.bmax, s.bbox_max);
+			cp3(d.wbmin, s.warped_bbox_min); cp3(d.wbmax, s.warped_bbox_max);
+			cp3(d.owbmin, s.original_warped_bbox_min); cp3(d.owbmax, s.original_warped_bbox_max);
+			d.n_tets = s.n_tets;
+			if (s.n_tets) {
+				if (!s.tet_lut_offsets || !s.tets || !s.vertices || !s.original_vertices || !s.original_bitfield || (s.n_lut_idx && !s.tet_lut_idx)) {
+					free_ops(c);
+					return fail(NSB_ERR_INVALID, "cage operator %d: missing arrays", i);
+				}
+				NsbStatus st;
+				if ((st = dev_copy(c, s.tet_lut_offsets, (size_t)NSB_GRID_CELLS + 1, &d.lut_off)) != NSB_OK) return st;
+				if ((st = dev_copy(c, s.tet_lut_idx, (size_t)s.n_lut_idx, &d.lut_idx)) != NSB_OK) return st;
+				if ((st = dev_copy(c, s.tets, (size_t)4 * s.n_tets, &d.tets)) != NSB_OK) return st;
+				if ((st = dev_copy(c, s.vertices, (size_t)3 * s.n_vertices, &d.verts)) != NSB_OK) return st;
+				if ((st = dev_copy(c, s.original_vertices, (size_t)3 * s.n_vertices, &d.orig_verts)) != NSB_OK) return st;
+				if ((st = dev_copy(c, s.local_rotations, (size_t)9 * s.n_tets, &d.rots)) != NSB_OK) return st;
+				if ((st = dev_copy(c, s.original_bitfield, (size_t)NSB_BITFIELD_BYTES, &d.obits)) != NSB_OK) return st;
+				if (s.boundary_shs && s.boundary_outside_density && s.boundary_residual_density) {
+					if ((st = dev_copy(c, s.boundary_shs, (size_t)27 * s.n_vertices, &d.shs)) != NSB_OK) return st;
+					if ((st = dev_copy(c, s.boundary_outside_density, (size_t)s.n_vertices, &d.od)) != NSB_OK) return st;
+					if ((st = dev_copy(c, s.boundary_residual_density, (size_t)s.n_vertices, &d.rd)) != NSB_OK) return st;
+					d.has_poisson_data = 1;
+				}
+				if (d.apply_poisson && d.has_poisson_data) any_poisson = 1;
+			}
+		} else if (s.type == NSB_OP_AFFINE) {
+			cpbox(d.sel, s.selection_box);
+			cpbox(d.dst, s.destination_box);
+			cp3(d.translation, s.translation);
+			cp3(d.scale, s.scale);
+			memcpy(d.rot, s.rotation, sizeof(d.rot));
+			d.hide_original = s.hide_original;
+			d.correct_dir = s.correct_dir;
+		} else {
+			free_ops(c);
+			return fail(NSB_ERR_INVALID, "operator %d: unknown type %d", i, s.type);
+		}
+	}
+	CU(cudaMalloc(&c->d_ops, sizeof(DevOp) * n));
+	CU(cudaMemcpy(c->d_ops, dev.data(), sizeof(DevOp) * n, cudaMemcpyHostToDevice));
+	c->n_ops = n;
+	c->any_poisson = any_poisson;
+	return NSB_OK;
+}
+
+// ---- frame conversion ---------------------------------------------------------------------------------
+static const uint32_t kSobolDir1[32] = {
+	0x80000000, 0xc0000000, 0xa0000000, 0xf0000000, 0x88000000, 0xcc000000, 0xaa000000, 0xff000000, 0x80800000, 0xc0c00000, 0xa0a00000,
+	0xf0f00000, 0x88880000, 0xcccc0000, 0xaaaa0000, 0xffff0000, 0x80008000, 0xc000c000, 0xa000a000, 0xf000f000, 0x88008800, 0xcc00cc00,
+	0xaa00aa00, 0xff00ff00, 0x80808080, 0xc0c0c0c0, 0xa0a0a0a0, 0xf0f0f0f0, 0x88888888, 0xcccccccc, 0xaaaaaaaa, 0xffffffff,
+};
+// ld_random_val_2d (random_val.cuh:278-282)
+static void host_ld_random_val_2d(uint32_t index, uint32_t seed, float* out) {
+	index = nested_uniform_scramble_base2(index, seed);
+	for (uint32_t dim = 0; dim < 2; ++dim) {
+		uint32_t X = 0;
+		for (uint32_t bit = 0; bit < 32; ++bit) {
+			uint32_t mask = (index >> bit) & 1u;
+			X ^= mask * (dim == 0 ? (0x80000000u >> bit) : kSobolDir1[bit]);
+		}
+		out[dim] = (float)nested_uniform_scramble_base2(X, hash_combine(seed, dim)) * 2.3283064365386963e-10f;
+	}
+}
+// ld_random_pixel_offset (random_val.cuh:317-322): the same for every pixel, so evaluated once here
+static void host_pixel_offset(uint32_t spp, float* off) {
+	float a[2], b[2];
+	host_ld_random_val_2d(0, 0xdeadbeefu, a);
+	host_ld_random_val_2d(spp, 0xdeadbeefu, b);
+	for (int i = 0; i < 2; ++i) {
+		volatile float s = 0.5f - a[i];
+		volatile float o = s + b[i];
+		off[i] = o - floorf(o);
+	}
+}
+
+static NsbStatus to_dev_frame(const NsbFrame* f, DevFrame* d) {
+	if (!f) return fail(NSB_ERR_INVALID, "frame is null");
+	if (f->width <= 0 || f->height <= 0 || (uint64_t)f->width * f->height > 0x7fffffffull / 786433ull * 786433ull) return fail(NSB_ERR_INVALID, "bad resolution %dx%d", f->width, f->height);
+	if (f->tile_world <= 0 || f->tile_rank < 0 || f->tile_rank >= f->tile_world) return fail(NSB_ERR_INVALID, "bad tile partition %d/%d", f->tile_rank, f->tile_world);
+	switch (f->render_mode) {
+		case NSB_RENDER_AO: case NSB_RENDER_SHADE: case NSB_RENDER_POSITIONS: case NSB_RENDER_DEPTH:
+		case NSB_RENDER_DISTANCE: case NSB_RENDER_STEPSIZE: case NSB_RENDER_COST: break;
+		default: return fail(NSB_ERR_UNSUPPORTED, "render mode %d is not covered (Normals/EncodingVis need network input gradients; Slice/Distortion are side paths)", f->render_mode);
+	}
+	if (f->rgb_activation < 0 || f->rgb_activation > 3 || f->density_activation < 0 || f->density_activation > 3) return fail(NSB_ERR_INVALID, "bad activation");
+	d->W = f->width; d->H = f->height;
+	d->fx = f->focal_length[0]; d->fy = f->focal_length[1];
+	d->cx = f->screen_center[0]; d->cy = f->screen_center[1];
+	memcpy(d->cam0, f->camera0, sizeof(d->cam0));
+	memcpy(d->cam1, f->camera1, sizeof(d->cam1));
+	memcpy(d->rs, f->rolling_shutter, sizeof(d->rs));
+	cp3(d->rmin, f->render_aabb_min); cp3(d->rmax, f->render_aabb_max);
+	cp3(d->tmin, f->train_aabb_min); cp3(d->tmax, f->train_aabb_max);
+	d->cone = f->cone_angle_constant;
+	d->min_T = f->min_transmittance;
+	d->depth_scale = f->depth_scale;
+	d->rgb_act = f->rgb_activation; d->density_act = f->density_activation; d->mode = f->render_mode;
+	d->spp = f->spp_index;
+	host_pixel_offset(f->snap_to_pixel_centers ? 0u : f->spp_index, d->pix_off);
+	d->apply_ops = f->apply_operators; d->poisson_target = f->poisson_target; d->linear_colors = f->linear_colors;
+	d->min_mip = f->min_mip < 0 ? 0 : (f->min_mip > 4 ? 4 : f->min_mip);
+	d->tile_rank = f->tile_rank; d->tile_world = f->tile_world;
+	d->tiles_x = (f->width + TILE_W - 1) / TILE_W;
+	d->tiles_y = (f->height + TILE_H - 1) / TILE_H;
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_dev, float* depth_dev, void* stream_) {
+	if (!c || !fb_dev || !depth_dev) return fail(NSB_ERR_INVALID, "null argument");
+	if (!c->has_model) return fail(NSB_ERR_STATE, "nsb_upload_model has not been called");
+	DevFrame f;
+	NsbStatus st = to_dev_frame(frame, &f);
+	if (st != NSB_OK) return st;
+	CU(cudaSetDevice(c->device));
+	cudaStream_t stream = (cudaStream_t)stream_;
+	CU(cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), stream));
+	CU(cudaMemsetAsync(c->d_stats, 0, ST_N * sizeof(unsigned long long), stream));
+	uint32_t n_tiles = (uint32_t)(f.tiles_x * f.tiles_y);
+	uint32_t my_tiles = (n_tiles + (uint32_t)f.tile_world - 1 - (uint32_t)f.tile_rank) / (uint32_t)f.tile_world;
+	uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
+	if (grid > my_tiles) grid = my_tiles > 0 ? my_tiles : 1;
+	CU(cudaEventRecord(c->ev0, stream));
+	k_render_fused<<<grid, 128, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
+	                                                         reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_tile_counter, c->d_stats);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->ev1, stream));
+	c->timed = true;
+	c->launches = 1;
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_render_host(NsbContext* c, const NsbFrame* frame, float* fb_host, float* depth_host) {
+	if (!c || !frame || !fb_host) return fail(NSB_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(c->device));
+	size_t n = (size_t)frame->width * (size_t)frame->height;
+	if (n == 0) return fail(NSB_ERR_INVALID, "empty frame");
+	if (n > c->fb_pixels) {
+		cudaFree(c->d_fb); cudaFree(c->d_depth);
+		c->d_fb = nullptr; c->d_depth = nullptr; c->fb_pixels = 0;
+		CU(cudaMalloc(&c->d_fb, n * 16));
+		CU(cudaMalloc(&c->d_depth, n * 4));
+		c->fb_pixels = n;
+	}
+	CU(cudaMemsetAsync(c->d_fb, 0, n * 16, c->stream));  // render_buffer.clear_frame (testbed.cu:2635)
+	CU(cudaMemsetAsync(c->d_depth, 0, n * 4, c->stream));
+	NsbStatus st = nsb_render(c, frame, c->d_fb, c->d_depth, c->stream);
+	if (st != NSB_OK) return st;
+	CU(cudaMemcpyAsync(fb_host, c->d_fb, n * 16, cudaMemcpyDeviceToHost, c->stream));
+	if (depth_host) CU(cudaMemcpyAsync(depth_host, c->d_depth, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_get_stats(NsbContext* c, NsbRenderStats* out) {
+	if (!c || !out) return fail(NSB_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(c->device));
+	memset(out, 0, sizeof(*out));
+	if (!c->timed) return NSB_OK;
+	CU(cudaEventSynchronize(c->ev1));
+	unsigned long long h[ST_N];
+	CU(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+	out->n_rays = h[ST_RAYS]; out->n_rays_alive = h[ST_ALIVE]; out->n_hit = h[ST_HIT]; out->n_samples = h[ST_SAMPLES]; out->n_old_samples = h[ST_OLD];
+	out->n_kernel_launches = c->launches;
+	CU(cudaEventElapsedTime(&out->gpu_ms, c->ev0, c->ev1));
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_tiles_for_rank(int32_t width, int32_t height, int32_t rank, int32_t world, uint32_t* n_tiles) {
+	if (!n_tiles || width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world) return fail(NSB_ERR_INVALID, "bad arguments");
+	uint32_t total = (uint32_t)(((width + TILE_W - 1) / TILE_W) * ((height + TILE_H - 1) / TILE_H));
+	*n_tiles = (total + (uint32_t)world - 1 - (uint32_t)rank) / (uint32_t)world;
+	return NSB_OK;
+}
+
+static NsbStatus pack_impl(NsbContext* c, const float* fb, const float* depth, int W, int H, int rank, int world, float* pr, float* pd, void* stream, int unpack) {
+	if (!c || !fb || !pr) return fail(NSB_ERR_INVALID, "null argument");
+	uint32_t mine = 0;
+	NsbStatus st = nsb_tiles_for_rank(W, H, rank, world, &mine);
+	if (st != NSB_OK) return st;
+	CU(cudaSetDevice(c->device));
+	int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
+	if (mine == 0) return NSB_OK;
+	k_pack_tiles<<<mine, TILE_PIXELS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(fb), depth, W, H, tiles_x, tiles_x * tiles_y, rank, world,
+	                                                            reinterpret_cast<float4*>(pr), pd, unpack);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_pack_tiles(NsbContext* c, const float* fb_dev, const float* depth_dev, int32_t W, int32_t H, int32_t rank, int32_t world,
+                                    float* dst_rgba, float* dst_depth, void* stream) {
+	return pack_impl(c, fb_dev, depth_dev, W, H, rank, world, dst_rgba, dst_depth, stream, 0);
+}
+extern "C" NsbStatus nsb_unpack_tiles(NsbContext* c, const float* src_rgba, const float* src_depth, int32_t W, int32_t H, int32_t rank, int32_t world,
+                                      float* fb_dev, float* depth_dev, void* stream) {
+	return pack_impl(c, fb_dev, depth_dev, W, H, rank, world, const_cast<float*>(src_rgba), const_cast<float*>(src_depth), stream, 1);
+}
+
+// ---- operator-level entry points -------------------------------------------------------------------------
+template <bool DENSITY_ONLY>
+static NsbStatus inference_impl(NsbContext* c, const float* coords, uint32_t n, uint16_t* out, uint32_t n_padded, void* stream) {
+	if (!c || !coords || !out) return fail(NSB_ERR_INVALID, "null argument");
+	if (!c->has_model) return fail(NSB_ERR_STATE, "nsb_upload_model has not been called");
+	if (n_padded < n || n_padded % 128 != 0) return fail(NSB_ERR_INVALID, "n_padded must be a multiple of 128 (tcnn::batch_size_granularity) and >= n");
+	if (n_padded == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	uint32_t grid = n_padded / 128;
+	uint32_t cap = (uint32_t)(c->sm_count * c->ctas_per_sm);
+	if (grid > cap) grid = cap;
+	k_inference<DENSITY_ONLY><<<grid, 128, sizeof(tc::TileSmem), (cudaStream_t)stream>>>(c->model, coords, n, reinterpret_cast<__half*>(out), n_padded);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_inference(NsbContext* c, const float* coords, uint32_t n, uint16_t* out, uint32_t n_padded, void* stream) {
+	return inference_impl<false>(c, coords, n, out, n_padded, stream);
+}
+extern "C" NsbStatus nsb_density(NsbContext* c, const float* coords, uint32_t n, uint16_t* out, uint32_t n_padded, void* stream) {
+	return inference_impl<true>(c, coords, n, out, n_padded, stream);
+}
+extern "C" NsbStatus nsb_encode(NsbContext* c, const float* coords, uint32_t n, uint16_t* out, uint32_t n_padded, void* stream) {
+	if (!c || !coords || !out) return fail(NSB_ERR_INVALID, "null argument");
+	if (!c->has_model) return fail(NSB_ERR_STATE, "nsb_upload_model has not been called");
+	if (n_padded < n) return fail(NSB_ERR_INVALID, "n_padded < n");
+	if (n == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	k_encode<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c->model, coords, n, reinterpret_cast<__half*>(out), n_padded);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_map_rays(NsbContext* c, float* coords, uint8_t* empty_mask, uint32_t n, void* stream) {
+	if (!c || !coords || !empty_mask) return fail(NSB_ERR_INVALID, "null argument");
+	if (n == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemsetAsync(empty_mask, 0, n, (cudaStream_t)stream));  // :2898
+	if (c->n_ops == 0) return NSB_OK;
+	k_map_rays<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c->d_ops, c->n_ops, coords, empty_mask, n);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_poisson_residuals(NsbContext* c, const float* coords, uint32_t n, float* sh, float* od, float* rd, void* stream) {
+	if (!c || !coords || !sh || !od || !rd) return fail(NSB_ERR_INVALID, "null argument");
+	if (n == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	k_poisson<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c->d_ops, c->n_ops, coords, n, sh, od, rd);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_march_trace(NsbContext* c, const NsbFrame* frame, const uint32_t* pixels, uint32_t n_pixels, uint32_t max_samples, float* rec,
+                                     uint32_t* idx, uint32_t* count, void* stream) {
+	if (!c || !pixels || !rec || !idx || !count) return fail(NSB_ERR_INVALID, "null argument");
+	DevFrame f;
+	NsbStatus st = to_dev_frame(frame, &f);
+	if (st != NSB_OK) return st;
+	if (n_pixels == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	k_march_trace<<<(n_pixels + 63) / 64, 64, 0, (cudaStream_t)stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, pixels, n_pixels, max_samples, rec, idx, count);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}

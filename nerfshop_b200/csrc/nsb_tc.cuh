@@ -1,0 +1,283 @@
+// nsb_tc.cuh — 5th-gen tensor core (tcgen05 / TMEM) plumbing for the fully fused 64-wide MLPs.
+//
+// Geometry: one CTA = 128 threads = 128 samples = the M dimension of every UMMA (M=128), thread t owns
+// sample row t, TMEM lane t, and (in the fused renderer) ray t. The five layers
+//     L1 32->64 (ReLU)  L2 64->16        (density MLP, base.json "network")
+//     L3 32->64 (ReLU)  L4 64->64 (ReLU)  L5 64->16   (rgb MLP, "rgb_network")
+// are 2+4+2+4+4 = 16 tcgen05.mma.kind::f16 instructions (K=16 each) with fp32 accumulators in TMEM.
+// Activations never leave the SM: encode/epilogue threads write fp16 rows straight into the UMMA
+// A-operand layout in shared memory, the weights (20 KB) are staged once per CTA by a bulk-TMA copy.
+//
+// Shared-memory operand layout (K-major, no swizzle = UMMA "interleave" canonical layout,
+// cute/atom/mma_traits_sm100.hpp: ((8,m),(T,2)):((1T,SBO),(1,LBO)) in 16-byte units):
+//   element (row r, k) of an [R x K] fp16 operand lives at  (k/8)*(R*16) + r*16 + (k%8)*2  bytes
+//   -> core matrix = 8 rows x 16 B contiguous (128 B); SBO (next 8 rows) = 128 B; LBO (next 8 k) = R*16 B.
+// A thread writing its own row touches 16 contiguous bytes per k-chunk, and the 32 lanes of a warp cover
+// 512 contiguous bytes: conflict-free stores without padding.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace nsb {
+namespace tc {
+
+constexpr uint32_t ROWS = 128;                    // samples per tile = UMMA M
+constexpr uint32_t A32_BYTES = 4 * ROWS * 16;     // [4 k-chunks][128][16 B]
+constexpr uint32_t A64_BYTES = 8 * ROWS * 16;
+// weight image: W1 [64x32], W2 [16x64], W3 [64x32], W4 [64x64], W5 [16x64], each in the operand layout above
+constexpr uint32_t W1_OFF = 0;
+constexpr uint32_t W2_OFF = W1_OFF + 64 * 32 * 2;
+constexpr uint32_t W3_OFF = W2_OFF + 16 * 64 * 2;
+constexpr uint32_t W4_OFF = W3_OFF + 64 * 32 * 2;
+constexpr uint32_t W5_OFF = W4_OFF + 64 * 64 * 2;
+constexpr uint32_t W_BYTES = W5_OFF + 16 * 64 * 2;  // 20480
+constexpr uint32_t TMEM_COLS = 64;
+
+struct __align__(128) TileSmem {
+	uint8_t w[W_BYTES];
+	uint8_t a32[A32_BYTES];
+	uint8_t a64[A64_BYTES];
+	uint64_t mma_bar;
+	uint64_t w_bar;
+	uint32_t tmem_base;
+	uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a broken pipeline traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	uint32_t addr = smem_u32(bar);
+	uint32_t done = 0;
+	for (uint32_t spins = 0; !done; ++spins) {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done)
+			: "r"(addr), "r"(parity)
+			: "memory");
+		if (spins > (1u << 22)) __trap();
+	}
+}
+// bulk TMA copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+	             "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+// generic-proxy shared stores -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {  // one full warp
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {  // the allocating warp
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32-bit, 16 consecutive columns: thread i of the warp gets lane (base_lane + i), columns c..c+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+		  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+		: "r"(taddr)
+		: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+	             : "r"(taddr)
+	             : "memory");
+}
+
+// ---- UMMA descriptors -----------------------------------------------------------------------------
+// cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), base_offset [49,52)=0, lbo_mode [52]=0, layout_type [61,64)=0 (SWIZZLE_NONE).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+	uint64_t d = 0;
+	d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+	d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+	d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+	d |= (uint64_t)1 << 46;
+	return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=F32 (c_format 1 @ [4,6)), A=B=F16 (0), both K-major (0),
+// N>>3 @ [17,23), M>>4 @ [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+		:
+		: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One layer: D[128 x N] = A[128 x K] * W[N x K]^T, issued by ONE thread; completion arrives on mma_bar.
+template <uint32_t N, uint32_t K>
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
+	constexpr uint32_t idesc = make_idesc(ROWS, N);
+#pragma unroll
+	for (uint32_t k = 0; k < K / 16; ++k) {
+		// one instruction consumes K=16 = two 8-wide k-chunks; chunk stride = rows*16 bytes
+		uint64_t ad = make_desc(a_addr + k * 2 * (ROWS * 16), ROWS * 16, 128);
+		uint64_t bd = make_desc(w_addr + k * 2 * (N * 16), N * 16, 128);
+		umma_f16(tmem_d, ad, bd, idesc, k > 0 ? 1u : 0u);
+	}
+	umma_commit(bar);
+}
+
+// ---- tile lifecycle -------------------------------------------------------------------------------
+// All 128 threads call; returns the TMEM base address (lane 0, column 0 of this CTA's 64 columns).
+__device__ __forceinline__ uint32_t tile_setup(TileSmem& s, const uint8_t* __restrict__ w_image) {
+	const uint32_t tid = threadIdx.x;
+	if (tid == 0) {
+		mbar_init(&s.mma_bar, 1);
+		mbar_init(&s.w_bar, 1);
+		fence_mbar_init();
+	}
+	if (tid < 32) tmem_alloc(&s.tmem_base, TMEM_COLS);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	if (tid == 0) {
+		mbar_expect_tx(&s.w_bar, W_BYTES);
+		bulk_g2s(s.w, w_image, W_BYTES, &s.w_bar);
+	}
+	mbar_wait(&s.w_bar, 0);
+	return *reinterpret_cast<volatile uint32_t*>(&s.tmem_base);
+}
+__device__ __forceinline__ void tile_teardown(TileSmem& s, uint32_t tmem_base) {
+	tc_fence_before();
+	__syncthreads();
+	if (threadIdx.x < 32) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- operand row stores ------------------------------------------------------------------------------
+// 8 consecutive fp16 (one 16-byte k-chunk) of this thread's row
+__device__ __forceinline__ void store_chunk(uint8_t* base, uint32_t chunk, uint32_t row, uint4 v) {
+	*reinterpret_cast<uint4*>(base + chunk * (ROWS * 16) + row * 16) = v;
+}
+__device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits) {
+	float a = fmaxf(__uint_as_float(a_bits), 0.0f), b = fmaxf(__uint_as_float(b_bits), 0.0f);
+	return pack_h2(__floats2half2_rn(a, b));
+}
+__device__ __forceinline__ uint32_t pack(uint32_t a_bits, uint32_t b_bits) {
+	return pack_h2(__floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits)));
+}
+
+// Epilogue of a 64-wide hidden layer: TMEM fp32 [row][0..63] -> ReLU -> fp16 -> a64 row (8 chunks)
+__device__ __forceinline__ void epilogue_hidden(TileSmem& s, uint32_t tmem_row, uint32_t row) {
+#pragma unroll
+	for (uint32_t q = 0; q < 4; ++q) {
+		uint32_t r[16];
+		tmem_ld16(tmem_row + q * 16, r);
+		tmem_wait_ld();
+		uint4 c0 = make_uint4(relu_pack(r[0], r[1]), relu_pack(r[2], r[3]), relu_pack(r[4], r[5]), relu_pack(r[6], r[7]));
+		uint4 c1 = make_uint4(relu_pack(r[8], r[9]), relu_pack(r[10], r[11]), relu_pack(r[12], r[13]), relu_pack(r[14], r[15]));
+		store_chunk(s.a64, 2 * q, row, c0);
+		store_chunk(s.a64, 2 * q + 1, row, c1);
+	}
+}
+
+// Runs the network on the 128 rows whose grid features are already in s.a32 (chunks 0-3).
+//   density_only: stop after L2 (NerfNetwork::density)
+//   dens[8]: the 16 fp16 outputs of the density MLP (packed half2), rgb[8]: the 16 outputs of the rgb MLP.
+// `sh` = this row's 16 SH values (8 half2), consumed between L2 and L3.
+// `phase` is the running parity of s.mma_bar (one flip per layer).
+__device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uint32_t& phase, const __half2* sh, bool density_only,
+                                            uint32_t* dens, uint32_t* rgb) {
+	const uint32_t tid = threadIdx.x;
+	const uint32_t row = tid;
+	const uint32_t tmem_row = tmem_base + ((tid & ~31u) << 16);  // lane field = first lane of this warp's quarter
+	const uint32_t a32 = smem_u32(s.a32), a64 = smem_u32(s.a64), w = smem_u32(s.w);
+
+	// ---- L1: a32 (32) -> 64
+	fence_async_smem();
+	tc_fence_before();
+	__syncthreads();
+	if (tid == 0) { tc_fence_after(); issue_layer<64, 32>(tmem_base, a32, w + W1_OFF, &s.mma_bar); }
+	mbar_wait(&s.mma_bar, phase); phase ^= 1;
+	tc_fence_after();
+	epilogue_hidden(s, tmem_row, row);
+
+	// ---- L2: a64 (64) -> 16
+	fence_async_smem();
+	tc_fence_before();
+	__syncthreads();
+	if (tid == 0) { tc_fence_after(); issue_layer<16, 64>(tmem_base, a64, w + W2_OFF, &s.mma_bar); }
+	mbar_wait(&s.mma_bar, phase); phase ^= 1;
+	tc_fence_after();
+	{
+		uint32_t r[16];
+		tmem_ld16(tmem_row, r);
+		tmem_wait_ld();
+#pragma unroll
+		for (int i = 0; i < 8; ++i) dens[i] = pack(r[2 * i], r[2 * i + 1]);
+	}
+	if (density_only) { tc_fence_before(); return; }
+	// rgb-network input: rows 0-15 = density MLP output, 16-31 = SH (nerf_network_full.h:52,67,79)
+	store_chunk(s.a32, 0, row, make_uint4(dens[0], dens[1], dens[2], dens[3]));
+	store_chunk(s.a32, 1, row, make_uint4(dens[4], dens[5], dens[6], dens[7]));
+	store_chunk(s.a32, 2, row, make_uint4(pack_h2(sh[0]), pack_h2(sh[1]), pack_h2(sh[2]), pack_h2(sh[3])));
+	store_chunk(s.a32, 3, row, make_uint4(pack_h2(sh[4]), pack_h2(sh[5]), pack_h2(sh[6]), pack_h2(sh[7])));
+
+	// ---- L3: a32 -> 64
+	fence_async_smem();
+	tc_fence_before();
+	__syncthreads();
+	if (tid == 0) { tc_fence_after(); issue_layer<64, 32>(tmem_base, a32, w + W3_OFF, &s.mma_bar); }
+	mbar_wait(&s.mma_bar, phase); phase ^= 1;
+	tc_fence_after();
+	epilogue_hidden(s, tmem_row, row);
+
+	// ---- L4: a64 -> 64
+	fence_async_smem();
+	tc_fence_before();
+	__syncthreads();
+	if (tid == 0) { tc_fence_after(); issue_layer<64, 64>(tmem_base, a64, w + W4_OFF, &s.mma_bar); }
+	mbar_wait(&s.mma_bar, phase); phase ^= 1;
+	tc_fence_after();
+	epilogue_hidden(s, tmem_row, row);
+
+	// ---- L5: a64 -> 16
+	fence_async_smem();
+	tc_fence_before();
+	__syncthreads();
+	if (tid == 0) { tc_fence_after(); issue_layer<16, 64>(tmem_base, a64, w + W5_OFF, &s.mma_bar); }
+	mbar_wait(&s.mma_bar, phase); phase ^= 1;
+	tc_fence_after();
+	{
+		uint32_t r[16];
+		tmem_ld16(tmem_row, r);
+		tmem_wait_ld();
+#pragma unroll
+		for (int i = 0; i < 8; ++i) rgb[i] = pack(r[2 * i], r[2 * i + 1]);
+	}
+	tc_fence_before();
+}
+
+}  // namespace tc
+}  // namespace nsb

@@ -1,0 +1,179 @@
+"""Python host mirror of the reference surfaces the render path is called through, over the C ABI.
+
+  NerfRenderer.render            <- Testbed::render_nerf            (testbed_nerf.cu:3066)
+  NerfRenderer.render_to_cpu     <- Testbed::render_to_cpu          (python_api.cu:129-175)
+  NerfRenderer.inference / density <- NerfNetwork::inference_mixed_precision / ::density
+  NerfRenderer.map_rays / poisson_residuals <- EditOperator::map_rays / ::compute_poisson_full_residuals
+  NerfRenderer.{add,reset}_edit_operator <- NerfTracer::{add,reset}_edit_operator (testbed.h:129-240)
+
+torch is used for device memory and streams only; every computation is a call into libnerfshop_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class NerfRenderer:
+    def __init__(self, device: int | None = None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise abi.NsbError("no CUDA device: nerfshop_b200 has no CPU fallback")
+        self.lib = abi.load_library()
+        self.device = torch.cuda.current_device() if device is None else device
+        self.ctx = C.c_void_p()
+        abi.check(self.lib, self.lib.nsb_create(self.device, C.byref(self.ctx)), "nsb_create")
+        self._ops = []
+        self._keep = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.nsb_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state -------------------------------------------------------------------------------------
+    def upload_model(self, desc: abi.NsbModelDesc, params_u16: np.ndarray):
+        p = np.ascontiguousarray(params_u16, dtype=np.uint16)
+        abi.check(self.lib, self.lib.nsb_upload_model(self.ctx, C.byref(desc), p.ctypes.data, p.size), "nsb_upload_model")
+
+    def upload_occupancy(self, bitfield: np.ndarray):
+        b = np.ascontiguousarray(bitfield, dtype=np.uint8)
+        abi.check(self.lib, self.lib.nsb_upload_occupancy(self.ctx, b.ctypes.data, b.size), "nsb_upload_occupancy")
+
+    def set_edit_operators(self, ops):
+        """ops: list of (NsbEditOp, keepalive) in m_edit_operators order."""
+        self._ops = list(ops or [])
+        if self._ops:
+            arr = (abi.NsbEditOp * len(self._ops))(*[o[0] for o in self._ops])
+            abi.check(self.lib, self.lib.nsb_set_edit_ops(self.ctx, arr, len(self._ops)), "nsb_set_edit_ops")
+        else:
+            abi.check(self.lib, self.lib.nsb_set_edit_ops(self.ctx, None, 0), "nsb_set_edit_ops")
+
+    def add_edit_operator(self, op):
+        self.set_edit_operators(self._ops + [op])
+
+    def reset_edit_operators(self):
+        self.set_edit_operators([])
+
+    # ---- the hot path ------------------------------------------------------------------------------------
+    def render(self, frame: abi.NsbFrame, fb=None, depth=None, stream=None):
+        """fb: float32 CUDA tensor [H, W, 4] (over-blended onto, like render_buffer.frame_buffer()); depth [H, W]."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        if fb is None:
+            fb = torch.zeros((frame.height, frame.width, 4), dtype=torch.float32, device=dev)
+        if depth is None:
+            depth = torch.zeros((frame.height, frame.width), dtype=torch.float32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+        abi.check(self.lib, self.lib.nsb_render(self.ctx, C.byref(frame), fb.data_ptr(), depth.data_ptr(), s), "nsb_render")
+        return fb, depth
+
+    def render_to_cpu(self, frame: abi.NsbFrame, fb_host=None, depth_host=None):
+        """Host-buffer entry point (pinned torch tensors or numpy arrays)."""
+        if fb_host is None:
+            fb_host = np.zeros((frame.height, frame.width, 4), np.float32)
+        if depth_host is None:
+            depth_host = np.zeros((frame.height, frame.width), np.float32)
+        fp = fb_host.data_ptr() if hasattr(fb_host, "data_ptr") else fb_host.ctypes.data
+        dp = depth_host.data_ptr() if hasattr(depth_host, "data_ptr") else depth_host.ctypes.data
+        abi.check(self.lib, self.lib.nsb_render_host(self.ctx, C.byref(frame), fp, dp), "nsb_render_host")
+        return fb_host, depth_host
+
+    def stats(self) -> abi.NsbRenderStats:
+        st = abi.NsbRenderStats()
+        abi.check(self.lib, self.lib.nsb_get_stats(self.ctx, C.byref(st)), "nsb_get_stats")
+        return st
+
+    # ---- multi-GPU framebuffer shards ------------------------------------------------------------------
+    def tiles_for_rank(self, width, height, rank, world) -> int:
+        n = C.c_uint32()
+        abi.check(self.lib, self.lib.nsb_tiles_for_rank(width, height, rank, world, C.byref(n)), "nsb_tiles_for_rank")
+        return n.value
+
+    def pack_tiles(self, fb, depth, rank, world, out_rgba, out_depth=None):
+        torch = _torch()
+        H, W = fb.shape[0], fb.shape[1]
+        s = torch.cuda.current_stream().cuda_stream
+        abi.check(self.lib, self.lib.nsb_pack_tiles(self.ctx, fb.data_ptr(), 0 if depth is None else depth.data_ptr(), W, H, rank, world,
+                                                    out_rgba.data_ptr(), 0 if out_depth is None else out_depth.data_ptr(), s), "nsb_pack_tiles")
+
+    def unpack_tiles(self, packed_rgba, packed_depth, rank, world, fb, depth=None):
+        torch = _torch()
+        H, W = fb.shape[0], fb.shape[1]
+        s = torch.cuda.current_stream().cuda_stream
+        abi.check(self.lib, self.lib.nsb_unpack_tiles(self.ctx, packed_rgba.data_ptr(), 0 if packed_depth is None else packed_depth.data_ptr(), W, H, rank, world,
+                                                      fb.data_ptr(), 0 if depth is None else depth.data_ptr(), s), "nsb_unpack_tiles")
+
+    # ---- operator-level entry points ---------------------------------------------------------------------
+    def _coords(self, coords):
+        torch = _torch()
+        c = torch.as_tensor(np.ascontiguousarray(coords, np.float32)) if not hasattr(coords, "data_ptr") else coords
+        return c.to(torch.device("cuda", self.device)).contiguous()
+
+    def _run_net(self, fn, name, coords, rows):
+        torch = _torch()
+        c = self._coords(coords)
+        n = c.shape[0]
+        n_pad = ((n + 127) // 128) * 128
+        out = torch.zeros((rows, n_pad), dtype=torch.int16, device=c.device)
+        abi.check(self.lib, fn(self.ctx, c.data_ptr(), n, out.data_ptr(), n_pad, torch.cuda.current_stream().cuda_stream), name)
+        torch.cuda.synchronize()
+        return out.cpu().numpy().view(np.uint16)[:, :n]
+
+    def inference(self, coords) -> np.ndarray:
+        return self._run_net(self.lib.nsb_inference, "nsb_inference", coords, 16)
+
+    def density(self, coords) -> np.ndarray:
+        return self._run_net(self.lib.nsb_density, "nsb_density", coords, 16)
+
+    def encode(self, coords) -> np.ndarray:
+        return self._run_net(self.lib.nsb_encode, "nsb_encode", coords, 32)
+
+    def map_rays(self, coords):
+        torch = _torch()
+        c = self._coords(coords).clone()
+        n = c.shape[0]
+        mask = torch.zeros(n, dtype=torch.uint8, device=c.device)
+        abi.check(self.lib, self.lib.nsb_map_rays(self.ctx, c.data_ptr(), mask.data_ptr(), n, torch.cuda.current_stream().cuda_stream), "nsb_map_rays")
+        torch.cuda.synchronize()
+        return c.cpu().numpy(), mask.cpu().numpy()
+
+    def poisson_residuals(self, coords):
+        torch = _torch()
+        c = self._coords(coords)
+        n = c.shape[0]
+        sh = torch.zeros((n, 27), dtype=torch.float32, device=c.device)
+        od = torch.zeros(n, dtype=torch.float32, device=c.device)
+        rd = torch.zeros(n, dtype=torch.float32, device=c.device)
+        abi.check(self.lib, self.lib.nsb_poisson_residuals(self.ctx, c.data_ptr(), n, sh.data_ptr(), od.data_ptr(), rd.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream), "nsb_poisson_residuals")
+        torch.cuda.synchronize()
+        return sh.cpu().numpy(), od.cpu().numpy(), rd.cpu().numpy()
+
+    def march_trace(self, frame: abi.NsbFrame, pixels: np.ndarray, max_samples: int):
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        p = torch.as_tensor(np.ascontiguousarray(pixels, np.uint32).view(np.int32)).to(dev)
+        n = p.numel()
+        rec = torch.zeros((n, max_samples, 5), dtype=torch.float32, device=dev)
+        idx = torch.zeros((n, max_samples, 2), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        abi.check(self.lib, self.lib.nsb_march_trace(self.ctx, C.byref(frame), p.data_ptr(), n, max_samples, rec.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream), "nsb_march_trace")
+        torch.cuda.synchronize()
+        return rec.cpu().numpy(), idx.cpu().numpy().view(np.uint32), cnt.cpu().numpy().view(np.uint32)

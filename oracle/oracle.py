@@ -1,0 +1,154 @@
+"""ctypes wrapper of oracle/libnerfshop_oracle.so — TEST INFRASTRUCTURE (see nerfshop_oracle.cpp header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The struct layouts are the public ones of include/nerfshop_b200.h (imported from nerfshop_b200.abi, types only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from nerfshop_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnerfshop_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "nerfshop_oracle.cpp")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+class OrcScene(C.Structure):
+    _fields_ = [
+        ("desc", abi.NsbModelDesc), ("params", C.c_void_p), ("n_params", C.c_uint64),
+        ("bitfield", C.c_void_p), ("ops", C.POINTER(abi.NsbEditOp)), ("n_ops", C.c_int32),
+    ]
+
+
+class OrcStats(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_uint64), ("n_rays_alive", C.c_uint64), ("n_hit", C.c_uint64),
+        ("n_samples", C.c_uint64), ("n_old_samples", C.c_uint64), ("threads", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        l = C.CDLL(LIB_PATH)
+        l.orc_f2h.restype = C.c_uint16
+        l.orc_f2h.argtypes = [C.c_float]
+        l.orc_h2f.restype = C.c_float
+        l.orc_h2f.argtypes = [C.c_uint16]
+        l.orc_ld_random_val.restype = C.c_float
+        l.orc_ld_random_val.argtypes = [C.c_uint32, C.c_uint32]
+        l.orc_pixel_offset.argtypes = [C.c_uint32, C.c_void_p]
+        l.orc_morton3D.restype = C.c_uint32
+        l.orc_morton3D.argtypes = [C.c_uint32] * 3
+        l.orc_mip_from_pos.argtypes = [C.c_float] * 3
+        l.orc_cascaded_grid_idx_at.restype = C.c_uint32
+        l.orc_cascaded_grid_idx_at.argtypes = [C.c_float] * 3 + [C.c_uint32]
+        l.orc_model_n_params.argtypes = [C.POINTER(abi.NsbModelDesc), C.POINTER(C.c_uint64)]
+        l.orc_level_table.argtypes = [C.POINTER(abi.NsbModelDesc)] + [C.c_void_p] * 4
+        l.orc_encode.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.c_void_p]
+        l.orc_inference.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        l.orc_map_rays.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_void_p, C.c_uint32]
+        l.orc_poisson_residuals.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.orc_march_trace.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.orc_render.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_void_p, C.POINTER(OrcStats), C.c_void_p]
+        l.orc_set_threads.argtypes = [C.c_int]
+        _lib = l
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Holds a scene (model params, occupancy bitfield, edit operators) for the CPU restatement."""
+
+    def __init__(self, desc: abi.NsbModelDesc, params_u16: np.ndarray, bitfield: np.ndarray | None, ops=None):
+        self.lib = lib()
+        self.params = np.ascontiguousarray(params_u16, dtype=np.uint16)
+        self.bitfield = None if bitfield is None else np.ascontiguousarray(bitfield, dtype=np.uint8)
+        self.scene = OrcScene()
+        self.scene.desc = desc
+        self.scene.params = self.params.ctypes.data
+        self.scene.n_params = self.params.size
+        self.scene.bitfield = None if self.bitfield is None else self.bitfield.ctypes.data
+        self.set_ops(ops)
+
+    def set_ops(self, ops):
+        """ops: list of (NsbEditOp, keepalive) or None. The structs hold host pointers into keepalive arrays."""
+        self._ops_keep = ops
+        if ops:
+            arr = (abi.NsbEditOp * len(ops))(*[o[0] for o in ops])
+            self._ops_arr = arr
+            self.scene.ops = C.cast(arr, C.POINTER(abi.NsbEditOp))
+            self.scene.n_ops = len(ops)
+        else:
+            self.scene.ops = None
+            self.scene.n_ops = 0
+
+    def encode(self, coords: np.ndarray) -> np.ndarray:
+        coords = np.ascontiguousarray(coords, np.float32)
+        n = coords.shape[0]
+        out = np.zeros((32, n), np.uint16)
+        assert self.lib.orc_encode(C.byref(self.scene), _ptr(coords), n, _ptr(out)) == 0
+        return out
+
+    def inference(self, coords: np.ndarray, density_only: bool = False) -> np.ndarray:
+        coords = np.ascontiguousarray(coords, np.float32)
+        n = coords.shape[0]
+        out = np.zeros((16, n), np.uint16)
+        assert self.lib.orc_inference(C.byref(self.scene), _ptr(coords), n, _ptr(out), int(density_only)) == 0
+        return out
+
+    def map_rays(self, coords: np.ndarray):
+        c = np.ascontiguousarray(coords, np.float32).copy()
+        mask = np.zeros(c.shape[0], np.uint8)
+        assert self.lib.orc_map_rays(C.byref(self.scene), _ptr(c), _ptr(mask), c.shape[0]) == 0
+        return c, mask
+
+    def poisson_residuals(self, coords: np.ndarray):
+        c = np.ascontiguousarray(coords, np.float32)
+        n = c.shape[0]
+        sh = np.zeros((n, 27), np.float32)
+        od = np.zeros(n, np.float32)
+        rd = np.zeros(n, np.float32)
+        assert self.lib.orc_poisson_residuals(C.byref(self.scene), _ptr(c), n, _ptr(sh), _ptr(od), _ptr(rd)) == 0
+        return sh, od, rd
+
+    def march_trace(self, frame: abi.NsbFrame, pixels: np.ndarray, max_samples: int):
+        pixels = np.ascontiguousarray(pixels, np.uint32)
+        n = pixels.size
+        rec = np.zeros((n, max_samples, 5), np.float32)
+        idx = np.zeros((n, max_samples, 2), np.uint32)
+        cnt = np.zeros(n, np.uint32)
+        assert self.lib.orc_march_trace(C.byref(self.scene), C.byref(frame), _ptr(pixels), n, max_samples, _ptr(rec), _ptr(idx), _ptr(cnt)) == 0
+        return rec, idx, cnt
+
+    def render(self, frame: abi.NsbFrame, background: np.ndarray | None = None, want_margin: bool = False):
+        W, H = frame.width, frame.height
+        fb = np.zeros((H, W, 4), np.float32) if background is None else np.ascontiguousarray(background, np.float32).copy()
+        depth = np.zeros((H, W), np.float32)
+        margin = np.zeros((H, W), np.float32) if want_margin else None
+        stats = OrcStats()
+        rc = self.lib.orc_render(C.byref(self.scene), C.byref(frame), _ptr(fb), _ptr(depth), C.byref(stats), None if margin is None else _ptr(margin))
+        assert rc == 0
+        return fb, depth, stats, margin
+
+
+def set_threads(n: int) -> int:
+    return lib().orc_set_threads(n)
