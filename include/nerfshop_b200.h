@@ -202,6 +202,10 @@ NsbStatus nsb_render_host(NsbContext* ctx, const NsbFrame* frame, float* fb_host
 /* Synchronises and returns the counters of the last render. */
 NsbStatus nsb_get_stats(NsbContext* ctx, NsbRenderStats* out);
 
+/* Diagnostics of the last nsb_render (not part of the reference surface): out[0..6] = MLP rounds summed over CTAs, and
+ * per-phase SM cycles of one thread per CTA summed over CTAs {acquire/march, encode, mlp, composite, total}, CTAs run. */
+NsbStatus nsb_debug_counters(NsbContext* ctx, uint64_t* out, int32_t n);
+
 /* Multi-GPU helpers: packed tile buffers for the single framebuffer gather.
  * nsb_tiles_for_rank gives how many 16x8 tiles (and so how many float4 = n_tiles*128) a rank owns. */
 NsbStatus nsb_tiles_for_rank(int32_t width, int32_t height, int32_t rank, int32_t world, uint32_t* n_tiles);

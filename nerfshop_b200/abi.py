@@ -92,7 +92,7 @@ class NsbRenderStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "nsb_abi_version", "nsb_last_error", "nsb_create", "nsb_destroy",
     "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_set_edit_ops",
-    "nsb_render", "nsb_render_host", "nsb_get_stats",
+    "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
     "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
     "nsb_build_tet_grid", "nsb_compute_mvc", "nsb_interpolate_with_mvc", "nsb_local_rotations",
@@ -110,7 +110,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("NSB_LIB_PATH") or LIB_PATH  # NSB_LIB_PATH: A/B builds of the same library
     if not os.path.exists(p):
         raise NsbError(
             f"{p} not found: build the sm_100a extension first (python -c 'import __graft_entry__ as g; g.build()'). "
@@ -131,6 +131,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_render.argtypes = [vp, C.POINTER(NsbFrame), vp, vp, vp]
     lib.nsb_render_host.argtypes = [vp, C.POINTER(NsbFrame), vp, vp]
     lib.nsb_get_stats.argtypes = [vp, C.POINTER(NsbRenderStats)]
+    lib.nsb_debug_counters.argtypes = [vp, C.POINTER(u64), i32]
     lib.nsb_tiles_for_rank.argtypes = [i32, i32, i32, i32, C.POINTER(u32)]
     lib.nsb_pack_tiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.nsb_unpack_tiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]

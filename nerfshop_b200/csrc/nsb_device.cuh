@@ -317,43 +317,75 @@ __device__ __forceinline__ bool next_occupied(const DevFrame& f, const uint8_t* 
 	}
 }
 
+// The same walk, resumable: at most `budget` empty voxels are skipped per call. The state of the walk is `t`
+// alone (always a point of the ray's dt lattice), so splitting it over several calls yields bit-identical samples.
+enum MarchResult { MARCH_FOUND = 0, MARCH_EXIT = 1, MARCH_PENDING = 2 };
+__device__ __forceinline__ MarchResult next_occupied_budget(const DevFrame& f, const uint8_t* __restrict__ bitfield, V3 o, V3 d, V3 idir,
+                                                            float& t, float& dt, V3& pos, int& budget) {
+	while (true) {
+		pos = madd3(d, t, o);
+		if (!box_contains(f.rmin, f.rmax, pos)) return MARCH_EXIT;
+		dt = calc_dt(t, f.cone);
+		uint32_t mip = (uint32_t)max(f.min_mip, mip_from_dt(dt, pos));
+		uint32_t cell = cascaded_grid_idx_at(pos, mip);
+		if (!bitfield || bitfield_at(cell, mip, bitfield)) return MARCH_FOUND;
+		if (budget <= 0) return MARCH_PENDING;
+		--budget;
+		t = advance_to_next_voxel(t, f.cone, pos, d, idir, GRIDSIZE >> mip);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // tiny-cuda-nn GridEncoding (HashGrid, F = 2, linear) — SURVEY.md Appendix B.
 // One level: 8 gathers of a __half2, result += (half)(weight * data) with fp16 accumulation.
 // ------------------------------------------------------------------------------------------------
+// tcnn grid_index: dense levels index x + y*res + z*res^2, the others hash the vertex (primes 1, 2654435761, 805459861).
+// Both are a handful of integer ops; the level kind is uniform across the launch, so this is a select, not a divergent branch.
+template <int MODE>
 __device__ __forceinline__ uint32_t grid_index(const DevLevel& L, uint32_t gx, uint32_t gy, uint32_t gz) {
-	uint32_t index;
-	if (L.hashed) {
-		index = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
-		index = L.mask ? (index & L.mask) : (index % L.size);
-	} else {
-		index = gx + gy * L.res + gz * L.res2;
-		if (index >= L.size) index %= L.size;
-	}
-	return index;
+	uint32_t h = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
+	h = L.mask ? (h & L.mask) : (h % L.size);
+	uint32_t d = gx + gy * L.res + gz * L.res2;
+	// `index % size`: a dense index is below res + res^2 + res^3 < 2*size, so one conditional subtraction is the modulo
+	d = d >= L.size ? d - L.size : d;
+	return L.hashed ? h : d;
 }
 
+// NL consecutive levels at once: all 8*NL gathers are issued before the first one is consumed (memory-level parallelism;
+// the walk is bound by L1/L2 gather throughput, not by arithmetic).
+// (Measured and rejected, profiles/README.md: fetching x-neighbour corner pairs with one 8-byte load when they share
+// an aligned slot — the extra index arithmetic and predication cost more than the ~25% fewer gathers saved.)
+template <int NL, int MODE>
+__device__ __forceinline__ void encode_levels(const DevLevel* __restrict__ L, const __half2* __restrict__ grid, float x, float y, float z, __half2* out) {
+	__half2 v[NL][8];
+	float wx[NL], wy[NL], wz[NL];
+#pragma unroll
+	for (int l = 0; l < NL; ++l) {
+		float px = fma_(L[l].scale, x, 0.5f), py = fma_(L[l].scale, y, 0.5f), pz = fma_(L[l].scale, z, 0.5f);
+		float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+		wx[l] = sub(px, fx); wy[l] = sub(py, fy); wz[l] = sub(pz, fz);
+		uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+		const __half2* base = grid + L[l].offset;
+#pragma unroll
+		for (int c = 0; c < 8; ++c) v[l][c] = __ldg(base + grid_index<MODE>(L[l], gx + (c & 1), gy + ((c >> 1) & 1), gz + ((c >> 2) & 1)));
+	}
+#pragma unroll
+	for (int l = 0; l < NL; ++l) {
+		float ax[2] = {sub(1.0f, wx[l]), wx[l]}, ay[2] = {sub(1.0f, wy[l]), wy[l]}, az[2] = {sub(1.0f, wz[l]), wz[l]};
+		__half2 acc = __floats2half2_rn(0.0f, 0.0f);
+#pragma unroll
+		for (int c = 0; c < 8; ++c) {
+			float w = mul(mul(ax[c & 1], ay[(c >> 1) & 1]), az[(c >> 2) & 1]);
+			float2 d = __half22float2(v[l][c]);
+			acc = __hadd2(acc, __floats2half2_rn(mul(w, d.x), mul(w, d.y)));  // result += (T)(weight * data), fp16 accumulate
+		}
+		out[l] = acc;
+	}
+}
 __device__ __forceinline__ __half2 encode_level(const DevLevel& L, const __half2* __restrict__ grid, float x, float y, float z) {
-	float px = fma_(L.scale, x, 0.5f), py = fma_(L.scale, y, 0.5f), pz = fma_(L.scale, z, 0.5f);
-	float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-	float wx = sub(px, fx), wy = sub(py, fy), wz = sub(pz, fz);
-	uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-	const __half2* base = grid + L.offset;
-	__half2 v[8];
-#pragma unroll
-	for (int c = 0; c < 8; ++c) {
-		uint32_t idx = grid_index(L, gx + (c & 1), gy + ((c >> 1) & 1), gz + ((c >> 2) & 1));
-		v[c] = __ldg(base + idx);
-	}
-	float ax[2] = {sub(1.0f, wx), wx}, ay[2] = {sub(1.0f, wy), wy}, az[2] = {sub(1.0f, wz), wz};
-	__half2 acc = __floats2half2_rn(0.0f, 0.0f);
-#pragma unroll
-	for (int c = 0; c < 8; ++c) {
-		float w = mul(mul(ax[c & 1], ay[(c >> 1) & 1]), az[(c >> 2) & 1]);
-		float2 d = __half22float2(v[c]);
-		acc = __hadd2(acc, __floats2half2_rn(mul(w, d.x), mul(w, d.y)));
-	}
-	return acc;
+	__half2 out;
+	encode_levels<1, 2>(&L, grid, x, y, z, &out);
+	return out;
 }
 
 // tcnn SphericalHarmonics degree 4 on 2*d-1 -> 16 fp16 packed as 8 half2

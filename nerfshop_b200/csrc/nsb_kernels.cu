@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -21,20 +22,20 @@
 
 using namespace nsb;
 
+#ifndef NSB_MIN_CTAS
+#define NSB_MIN_CTAS 3  // resident CTAs per SM the fused kernel is compiled for (register cap = 65536 / (128 * NSB_MIN_CTAS))
+#endif
+
 // =====================================================================================================
 // fused persistent renderer
 // =====================================================================================================
-struct RenderSmem {
-	tc::TileSmem tile;
-	uint32_t cur_tile;  // linear 16x8 tile index this CTA is currently handing out pixels from
-	uint32_t taken;     // pixels of cur_tile handed out so far (>= 128: exhausted)
-	uint32_t no_more;   // the global tile queue is empty
-	uint32_t pad;
-};
+struct RayRec { uint32_t pix; float t; };  // a ray that entered the AABB and found occupied space: pixel + first sample t
 
-enum { ST_RAYS = 0, ST_ALIVE = 1, ST_HIT = 2, ST_SAMPLES = 3, ST_OLD = 4, ST_N = 5 };
+enum { ST_RAYS = 0, ST_ALIVE = 1, ST_HIT = 2, ST_SAMPLES = 3, ST_OLD = 4, ST_ROUNDS = 5, ST_CYC_ACQUIRE = 6, ST_CYC_ENCODE = 7, ST_CYC_MLP = 8,
+       ST_CYC_COMPOSITE = 9, ST_CYC_TOTAL = 10, ST_CTAS = 11, ST_N = 12 };
+constexpr int DDA_BUDGET = 8;   // empty voxels a lane may skip per MLP round before it yields (latency bound of a round)
 
-// tile slot -> pixel: the four warps of a CTA each cover an 8x4 block so that the 32 lanes of a warp stay
+// tile slot -> pixel: the four warps of a 16x8 tile each cover an 8x4 block so that the 32 lanes of a warp stay
 // spatially compact (coherent hash-grid and occupancy lookups)
 __device__ __forceinline__ bool tile_pixel(const DevFrame& f, uint32_t tile, uint32_t slot, uint32_t& px, uint32_t& py) {
 	uint32_t tx = tile % (uint32_t)f.tiles_x, ty = tile / (uint32_t)f.tiles_x;
@@ -44,42 +45,88 @@ __device__ __forceinline__ bool tile_pixel(const DevFrame& f, uint32_t tile, uin
 	return px < (uint32_t)f.W && py < (uint32_t)f.H;
 }
 
-// grid features of one sample -> this thread's row of the A operand (4 chunks x 8 fp16)
-__device__ __forceinline__ void encode_to_a32(tc::TileSmem& s, const DevModel& m, bool valid, V3 pw, uint32_t row) {
-#pragma unroll
-	for (int c = 0; c < 4; ++c) {
-		uint32_t h[4];
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			__half2 v = __floats2half2_rn(0.0f, 0.0f);
-			if (valid) v = encode_level(m.levels[4 * c + j], m.grid, pw.x, pw.y, pw.z);
-			h[j] = tc::pack_h2(v);
+// Stage 1 (massively parallel, one thread per pixel of this rank's tiles):
+// init_rays_with_payload_kernel_nerf (testbed_nerf.cu:2512) + advance_pos_nerf (:557) + the alive-ray compaction
+// of compact_kernel_nerf (:2485), with warp-aggregated atomics instead of one global atomic per ray.
+// The long empty-space walk to a ray's first occupied sample is a serial chain of dependent occupancy loads;
+// here it is hidden by running every ray of the frame concurrently instead of stalling an MLP round.
+__global__ void __launch_bounds__(256) k_prepare_rays(const DevFrame f, const uint8_t* __restrict__ bitfield, float* __restrict__ depth_out,
+                                                      RayRec* __restrict__ list, uint32_t* __restrict__ n_queued, uint32_t n_local_pixels,
+                                                      unsigned long long* __restrict__ stats) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool queued = false, is_ray = false, entered = false;
+	uint32_t pix = 0;
+	float t = 0.0f;
+	if (i < n_local_pixels) {
+		uint32_t tile = (uint32_t)f.tile_rank + (i / (uint32_t)TILE_PIXELS) * (uint32_t)f.tile_world;
+		uint32_t px, py;
+		if (tile_pixel(f, tile, i % (uint32_t)TILE_PIXELS, px, py)) {
+			is_ray = true;
+			pix = px + (uint32_t)f.W * py;
+			depth_out[pix] = 1e10f;  // :2581
+			Ray r;
+			if (make_ray(f, px, py, r)) {
+				entered = true;
+				V3 idir = v3(div_(1.0f, r.d.x), div_(1.0f, r.d.y), div_(1.0f, r.d.z));
+				t = fma_(ld_random_val(f.spp, pix * 786433u), calc_dt(r.t, f.cone), r.t);  // advance_pos_nerf :585
+				float dt; V3 pos; uint32_t mip, cell;
+				queued = next_occupied(f, bitfield, r.o, r.d, idir, t, dt, pos, mip, cell);
+			}
 		}
-		tc::store_chunk(s.a32, c, row, make_uint4(h[0], h[1], h[2], h[3]));
+	}
+	const unsigned lane = threadIdx.x & 31u;
+	unsigned m = __ballot_sync(0xffffffffu, queued);
+	unsigned mr = __ballot_sync(0xffffffffu, is_ray), me = __ballot_sync(0xffffffffu, entered);
+	uint32_t base = 0;
+	if (lane == 0) {
+		if (m) base = atomicAdd(n_queued, (uint32_t)__popc(m));
+		if (mr) atomicAdd(stats + ST_RAYS, (unsigned long long)__popc(mr));
+		if (me) atomicAdd(stats + ST_ALIVE, (unsigned long long)__popc(me));
+	}
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (queued) {
+		RayRec rr;
+		rr.pix = pix;
+		rr.t = t;
+		list[base + __popc(m & ((1u << lane) - 1u))] = rr;
+	}
+}
+
+// grid features of one sample -> this thread's row of the A operand (4 chunks x 8 fp16)
+// Code size matters here: the fused kernel's hot loop has to live in the SM's instruction cache (profiles/README.md:
+// the first, fully unrolled version was 504 KB of SASS and stalled on instruction fetch). One loop body = 2 levels
+// (16 gathers in flight per thread), 8 iterations.
+__device__ __forceinline__ void encode_to_a32(tc::TileSmem& s, const DevModel& m, bool valid, V3 pw, uint32_t row) {
+#pragma unroll 1
+	for (int g = 0; g < MAX_LEVELS / 2; ++g) {
+		__half2 h[2];
+		h[0] = h[1] = __floats2half2_rn(0.0f, 0.0f);
+		if (valid) encode_levels<2, 2>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
+		// levels 2g, 2g+1 = fp16 features 4g..4g+3 = half of k-chunk g/2
+		*reinterpret_cast<uint2*>(s.a32 + (g >> 1) * (tc::ROWS * 16) + row * 16 + (g & 1) * 8) = make_uint2(tc::pack_h2(h[0]), tc::pack_h2(h[1]));
 	}
 }
 
 __device__ __forceinline__ float h_lo(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed & 0xffffu))); }
 __device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed >> 16))); }
 
-__global__ void __launch_bounds__(128) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
+// Stage 2 (persistent, 128 threads = 128 ray slots = 128 MMA rows per CTA): every round each live ray contributes
+// ONE sample; samples go deform -> hash encode -> tcgen05 MLPs -> composite inside the SM; a finished ray is shaded
+// into the framebuffer and its slot refilled from the queue (warp-aggregated fetch, so rays that were refilled
+// together — neighbouring pixels that die on the same surface — stay together in a warp).
+__global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
-                                                      float4* __restrict__ fb, float* __restrict__ depth_out, uint32_t* tile_counter,
-                                                      unsigned long long* __restrict__ stats) {
+                                                      float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
+                                                      const uint32_t* __restrict__ n_queued_ptr, uint32_t* fetch_counter,
+                                                      unsigned long long* __restrict__ stats, const int refill_thr, const int dda_budget) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
-	RenderSmem& S = *reinterpret_cast<RenderSmem*>(smem_raw);
+	tc::TileSmem& S = *reinterpret_cast<tc::TileSmem*>(smem_raw);
 	const uint32_t tid = threadIdx.x;
-	const uint32_t n_tiles = (uint32_t)(f.tiles_x * f.tiles_y);
+	const uint32_t lane = tid & 31u;
+	const uint32_t n_queued = *n_queued_ptr;
+	if (blockIdx.x * 128u >= n_queued && blockIdx.x > 0) return;  // nothing this CTA could ever fetch
 
-	const uint32_t tmem_base = tc::tile_setup(S.tile, m.w_image);
-	if (tid == 0) {
-		uint32_t t = atomicAdd(tile_counter, 1u);
-		uint32_t tile = (uint32_t)f.tile_rank + t * (uint32_t)f.tile_world;
-		S.cur_tile = tile;
-		S.no_more = tile >= n_tiles ? 1u : 0u;
-		S.taken = tile >= n_tiles ? (uint32_t)TILE_PIXELS : 0u;
-	}
-	__syncthreads();
+	const uint32_t tmem_base = tc::tile_setup(S, m.w_image);
 
 	const bool ops_on = f.apply_ops && n_ops > 0;
 	const float sat = 1.0f - f.min_T;  // rendering_min_transmittance test of composite_kernel_nerf :951
@@ -87,13 +134,16 @@ __global__ void __launch_bounds__(128) k_render_fused(const DevFrame f, const De
 	const V3 cam_org = v3(f.cam1[9], f.cam1[10], f.cam1[11]);
 
 	// ray state (registers)
-	bool alive = false;
+	bool alive = false, exhausted = false;
 	V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), idir = v3(0, 0, 0);
 	float t = 0.0f;
 	float cr = 0, cg = 0, cb = 0, ca = 0, ray_depth = 0, max_weight = 0;
 	uint32_t pix = 0, n_steps = 0;
-	unsigned long long c_rays = 0, c_alive = 0, c_hit = 0, c_samples = 0, c_old = 0;
+	unsigned long long c_hit = 0, c_samples = 0, c_old = 0;
 	uint32_t phase = 0;
+	// phase profile (thread 0 of each CTA; a handful of clock reads per round)
+	long long cyc_acq = 0, cyc_enc = 0, cyc_mlp = 0, cyc_comp = 0, n_rounds = 0;
+	const long long cyc_start = clock64();
 
 	// shade_kernel_nerf (:2464-2482) for the ray this thread just finished (compact_kernel_nerf :2503 filter)
 	auto finish = [&](bool left_aabb) {
@@ -114,49 +164,45 @@ __global__ void __launch_bounds__(128) k_render_fused(const DevFrame f, const De
 	};
 
 	for (;;) {
-		if (tid == 0 && S.taken >= (uint32_t)TILE_PIXELS && !S.no_more) {
-			uint32_t tq = atomicAdd(tile_counter, 1u);
-			uint32_t tile = (uint32_t)f.tile_rank + tq * (uint32_t)f.tile_world;
-			if (tile >= n_tiles) {
-				S.no_more = 1u;
-			} else {
-				S.cur_tile = tile;
-				__threadfence_block();
-				S.taken = 0u;
-			}
-		}
-		const int any_alive = __syncthreads_or(alive ? 1 : 0);
-		if (!any_alive && *reinterpret_cast<volatile uint32_t*>(&S.no_more)) break;
+		if (!__syncthreads_or((alive || !exhausted) ? 1 : 0)) break;
+		const long long c0 = clock64();
 
 		// ---- acquire one occupied sample for this thread (refill the ray slot when it is free) ----
 		bool has_sample = false;
 		float dt = 0.0f;
 		V3 pos = v3(0, 0, 0);
+		int budget = dda_budget;
+		// Coherent refill: free lanes wait until the warp is down to <= refill_thr live rays and then refill TOGETHER
+		// with consecutive queue entries (= neighbouring pixels), so the lanes of a warp gather from the same few
+		// hash-grid cells on the coarse and middle levels instead of 32 unrelated cache lines per instruction.
+		const bool may_refill = __popc(__ballot_sync(0xffffffffu, alive)) <= refill_thr;
 		for (;;) {
 			if (!alive) {
-				if (*reinterpret_cast<volatile uint32_t*>(&S.taken) >= (uint32_t)TILE_PIXELS) break;
-				uint32_t slot = atomicAdd(&S.taken, 1u);
-				if (slot >= (uint32_t)TILE_PIXELS) break;
-				uint32_t px, py;
-				if (!tile_pixel(f, *reinterpret_cast<volatile uint32_t*>(&S.cur_tile), slot, px, py)) continue;
-				pix = px + (uint32_t)f.W * py;
-				depth_out[pix] = 1e10f;  // :2581
-				++c_rays;
+				if (exhausted || !may_refill) break;
+				// warp-aggregated fetch: the lanes that need a ray right now take consecutive queue entries
+				const unsigned grp = __activemask();
+				const int leader = __ffs(grp) - 1;
+				uint32_t base = 0;
+				if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(grp));
+				base = __shfl_sync(grp, base, leader);
+				const uint32_t qi = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+				if (qi >= n_queued) { exhausted = true; break; }
+				const RayRec rr = list[qi];
+				pix = rr.pix;
 				Ray r;
-				if (!make_ray(f, px, py, r)) continue;
-				++c_alive;
+				make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
 				ro = r.o; rd = r.d;
 				idir = v3(div_(1.0f, rd.x), div_(1.0f, rd.y), div_(1.0f, rd.z));
-				t = fma_(ld_random_val(f.spp, pix * 786433u), calc_dt(r.t, f.cone), r.t);  // advance_pos_nerf :585
+				t = rr.t;
 				cr = cg = cb = ca = 0.0f;
 				ray_depth = 0.0f; max_weight = 0.0f; n_steps = 0;
 				alive = true;
 			}
 			if (n_steps >= MARCH_ITER - 1) { alive = false; continue; }  // still marching after MARCH_ITER steps: dropped (:2812)
-			uint32_t mip, cell;
-			if (!next_occupied(f, bitfield, ro, rd, idir, t, dt, pos, mip, cell)) { finish(true); continue; }
-			has_sample = true;
-			break;
+			const MarchResult mr = next_occupied_budget(f, bitfield, ro, rd, idir, t, dt, pos, budget);
+			if (mr == MARCH_FOUND) { has_sample = true; break; }
+			if (mr == MARCH_EXIT) { finish(true); continue; }
+			break;  // MARCH_PENDING: resume next round
 		}
 
 		// ---- network inputs: generate_next_nerf_network_inputs :690 ----
@@ -184,24 +230,31 @@ __global__ void __launch_bounds__(128) k_render_fused(const DevFrame f, const De
 			}
 		}
 
-		// ---- "old" density: only read by the poisson-target blend (:773), so only evaluated there ----
+		// ---- encode + fused MLPs. Pass 0 (rare) is the "old" density on the un-mapped position: the reference runs a second
+		// full inference every round (:2892) but only the membrane's poisson-target blend ever reads it (:773), so it is
+		// evaluated only in rounds where some lane needs it, density MLP only. Pass 1 is the real sample. One code copy.
 		float sigma_old_raw = 0.0f;
-		if (ops_on && any_poisson && f.poisson_target) {
-			if (__syncthreads_or(need_old ? 1 : 0)) {
-				uint32_t dens_old[8], dummy[8];
-				encode_to_a32(S.tile, m, need_old, pw_old, tid);
-				tc::run_network(S.tile, tmem_base, phase, nullptr, true, dens_old, dummy);
-				sigma_old_raw = h_lo(dens_old[0]);
+		uint32_t dens[8], rgbo[8];
+		__half2 sh[8];
+		encode_sh4(dw, sh);
+		int first_pass = 1;
+		if (ops_on && any_poisson && f.poisson_target) first_pass = __syncthreads_or(need_old ? 1 : 0) ? 0 : 1;
+		const long long c1 = clock64();
+		long long enc_cycles = 0;
+#pragma unroll 1
+		for (int pass = first_pass; pass < 2; ++pass) {
+			const bool old_pass = pass == 0;
+			const long long e0 = clock64();
+			encode_to_a32(S, m, old_pass ? need_old : has_sample, old_pass ? pw_old : pw, tid);
+			enc_cycles += clock64() - e0;
+			tc::run_network(S, tmem_base, phase, sh, old_pass, dens, rgbo);
+			if (old_pass) {
+				sigma_old_raw = h_lo(dens[0]);
 				if (need_old) ++c_old;
 			}
 		}
-
-		// ---- encode + fused MLPs ----
-		uint32_t dens[8], rgbo[8];
-		__half2 sh[8];
-		encode_to_a32(S.tile, m, has_sample, pw, tid);
-		encode_sh4(dw, sh);
-		tc::run_network(S.tile, tmem_base, phase, sh, false, dens, rgbo);
+		const long long c2 = c1 + enc_cycles;
+		const long long c3 = clock64();
 
 		// ---- composite_kernel_nerf :750-955 for this one sample ----
 		if (has_sample) {
@@ -254,17 +307,28 @@ __global__ void __launch_bounds__(128) k_render_fused(const DevFrame f, const De
 				finish(false);
 			}
 		}
+		cyc_acq += c1 - c0; cyc_enc += c2 - c1; cyc_mlp += c3 - c2; cyc_comp += clock64() - c3; ++n_rounds;
 	}
 
-	tc::tile_teardown(S.tile, tmem_base);
+	tc::tile_teardown(S, tmem_base);
+	if (tid == 0) {
+		atomicAdd(stats + ST_ROUNDS, (unsigned long long)n_rounds);
+		atomicAdd(stats + ST_CYC_ACQUIRE, (unsigned long long)cyc_acq);
+		atomicAdd(stats + ST_CYC_ENCODE, (unsigned long long)cyc_enc);
+		atomicAdd(stats + ST_CYC_MLP, (unsigned long long)cyc_mlp);
+		atomicAdd(stats + ST_CYC_COMPOSITE, (unsigned long long)cyc_comp);
+		atomicAdd(stats + ST_CYC_TOTAL, (unsigned long long)(clock64() - cyc_start));
+		atomicAdd(stats + ST_CTAS, 1ull);
+	}
 
 	// counters: warp reduce, one atomic per warp
-	unsigned long long c[ST_N] = {c_rays, c_alive, c_hit, c_samples, c_old};
+	unsigned long long c[3] = {c_hit, c_samples, c_old};
+	const int slot[3] = {ST_HIT, ST_SAMPLES, ST_OLD};
 #pragma unroll
-	for (int k = 0; k < ST_N; ++k) {
+	for (int k = 0; k < 3; ++k) {
 		unsigned long long v = c[k];
 		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-		if ((tid & 31u) == 0 && v) atomicAdd(stats + k, v);
+		if (lane == 0 && v) atomicAdd(stats + slot[k], v);
 	}
 }
 
@@ -310,11 +374,15 @@ __global__ void k_encode(const DevModel m, const float* __restrict__ coords, uin
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	float x = coords[7 * (size_t)i], y = coords[7 * (size_t)i + 1], z = coords[7 * (size_t)i + 2];
-#pragma unroll 4
-	for (uint32_t l = 0; l < MAX_LEVELS; ++l) {
-		__half2 v = encode_level(m.levels[l], m.grid, x, y, z);
-		out[(size_t)(2 * l) * n_padded + i] = __low2half(v);
-		out[(size_t)(2 * l + 1) * n_padded + i] = __high2half(v);
+#pragma unroll 1
+	for (uint32_t g = 0; g < MAX_LEVELS / 2; ++g) {
+		__half2 v[2];
+		encode_levels<2, 2>(m.levels + 2 * g, m.grid, x, y, z, v);
+#pragma unroll
+		for (uint32_t j = 0; j < 2; ++j) {
+			out[(size_t)(4 * g + 2 * j) * n_padded + i] = __low2half(v[j]);
+			out[(size_t)(4 * g + 2 * j + 1) * n_padded + i] = __high2half(v[j]);
+		}
 	}
 }
 
@@ -421,8 +489,12 @@ struct NsbContext {
 	int n_ops = 0;
 	int any_poisson = 0;
 	std::vector<void*> op_allocs;
-	uint32_t* d_tile_counter = nullptr;
+	uint32_t* d_counters = nullptr;  // [0] rays queued by k_prepare_rays, [1] fetch cursor of k_render_fused
 	unsigned long long* d_stats = nullptr;
+	RayRec* d_list = nullptr;
+	size_t list_capacity = 0;
+	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
+	int dda_budget = DDA_BUDGET;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	bool timed = false;
 	uint32_t launches = 0;
@@ -488,19 +560,37 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	NsbContext* c = new NsbContext();
 	c->device = device;
 	c->sm_count = prop.multiProcessorCount;
-	CU(cudaMalloc(&c->d_tile_counter, sizeof(uint32_t)));
+	CU(cudaMalloc(&c->d_counters, 2 * sizeof(uint32_t)));
 	CU(cudaMalloc(&c->d_stats, ST_N * sizeof(unsigned long long)));
 	CU(cudaMemset(c->d_stats, 0, ST_N * sizeof(unsigned long long)));
 	CU(cudaEventCreate(&c->ev0));
 	CU(cudaEventCreate(&c->ev1));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RenderSmem)));
+	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
 	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
 	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
+	// Persistent grid = SMs x resident CTAs. Residency is bounded by registers (128/thread -> 4), shared memory
+	// (45 KB -> 5 of 227 KB; the carve-out is requested explicitly, the default heuristic picks a small one) and
+	// TMEM (64 of 512 columns per CTA -> 8).
+	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	int occ = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_fused, 128, sizeof(RenderSmem)));
-	// TMEM: 512 columns per SM, 64 per CTA
-	c->ctas_per_sm = occ < 1 ? 1 : (occ > 8 ? 8 : occ);
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_fused, 128, sizeof(tc::TileSmem)));
+	cudaFuncAttributes fa;
+	CU(cudaFuncGetAttributes(&fa, k_render_fused));
+	int by_regs = fa.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fa.numRegs * 128)) : 4;
+	int by_smem = (int)(prop.sharedMemPerMultiprocessor / (sizeof(tc::TileSmem) + 1024));
+	int want = by_regs < by_smem ? by_regs : by_smem;
+	if (want > 8) want = 8;
+	if (want < 1) want = 1;
+	c->ctas_per_sm = want;
+	if (const char* e = getenv("NSB_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->ctas_per_sm = v; }
+	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
+	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
+	if (getenv("NSB_VERBOSE"))
+		fprintf(stderr, "[nsb] device %d: %d SMs, occupancy API %d, regs %d -> %d, smem %zu -> %d, using %d CTAs/SM\n", device, c->sm_count, occ, fa.numRegs, by_regs,
+		        sizeof(tc::TileSmem), by_smem, c->ctas_per_sm);
 	*out = c;
 	return NSB_OK;
 }
@@ -520,7 +610,7 @@ extern "C" NsbStatus nsb_destroy(NsbContext* c) {
 	cudaDeviceSynchronize();
 	free_ops(c);
 	cudaFree(c->d_grid); cudaFree(c->d_wimage); cudaFree(c->d_wrow); cudaFree(c->d_bitfield);
-	cudaFree(c->d_tile_counter); cudaFree(c->d_stats); cudaFree(c->d_fb); cudaFree(c->d_depth);
+	cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_fb); cudaFree(c->d_depth); cudaFree(c->d_list);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -729,19 +819,33 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 	if (st != NSB_OK) return st;
 	CU(cudaSetDevice(c->device));
 	cudaStream_t stream = (cudaStream_t)stream_;
-	CU(cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), stream));
-	CU(cudaMemsetAsync(c->d_stats, 0, ST_N * sizeof(unsigned long long), stream));
 	uint32_t n_tiles = (uint32_t)(f.tiles_x * f.tiles_y);
 	uint32_t my_tiles = (n_tiles + (uint32_t)f.tile_world - 1 - (uint32_t)f.tile_rank) / (uint32_t)f.tile_world;
-	uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
-	if (grid > my_tiles) grid = my_tiles > 0 ? my_tiles : 1;
+	size_t n_local = (size_t)my_tiles * TILE_PIXELS;
+	if (n_local > c->list_capacity) {
+		CU(cudaStreamSynchronize(stream));
+		cudaFree(c->d_list);
+		c->d_list = nullptr; c->list_capacity = 0;
+		CU(cudaMalloc(&c->d_list, n_local * sizeof(RayRec)));
+		c->list_capacity = n_local;
+	}
 	CU(cudaEventRecord(c->ev0, stream));
-	k_render_fused<<<grid, 128, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
-	                                                         reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_tile_counter, c->d_stats);
-	CU(cudaGetLastError());
+	CU(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(uint32_t), stream));
+	CU(cudaMemsetAsync(c->d_stats, 0, ST_N * sizeof(unsigned long long), stream));
+	if (n_local > 0) {
+		k_prepare_rays<<<(unsigned)((n_local + 255) / 256), 256, 0, stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, depth_dev, c->d_list, c->d_counters,
+		                                                                   (uint32_t)n_local, c->d_stats);
+		CU(cudaGetLastError());
+		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
+		if (grid > my_tiles) grid = my_tiles;
+		k_render_fused<<<grid, 128, sizeof(tc::TileSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
+		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
+		                                                          c->refill_thr, c->dda_budget);
+		CU(cudaGetLastError());
+	}
 	CU(cudaEventRecord(c->ev1, stream));
 	c->timed = true;
-	c->launches = 1;
+	c->launches = 2;
 	return NSB_OK;
 }
 
@@ -781,6 +885,18 @@ extern "C" NsbStatus nsb_get_stats(NsbContext* c, NsbRenderStats* out) {
 	return NSB_OK;
 }
 
+// Diagnostic counters of the last render: rounds (CTA x MLP rounds), and thread-0 cycles per phase summed over CTAs:
+// {rounds, acquire, encode, mlp, composite, total, ctas}
+extern "C" NsbStatus nsb_debug_counters(NsbContext* c, uint64_t* out, int32_t n) {
+	if (!c || !out || n < 7) return fail(NSB_ERR_INVALID, "need room for 7 counters");
+	CU(cudaSetDevice(c->device));
+	if (c->timed) CU(cudaEventSynchronize(c->ev1));
+	unsigned long long h[ST_N];
+	CU(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 7; ++i) out[i] = h[ST_ROUNDS + i];
+	return NSB_OK;
+}
+
 extern "C" NsbStatus nsb_tiles_for_rank(int32_t width, int32_t height, int32_t rank, int32_t world, uint32_t* n_tiles) {
 	if (!n_tiles || width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world) return fail(NSB_ERR_INVALID, "bad arguments");
 	uint32_t total = (uint32_t)(((width + TILE_W - 1) / TILE_W) * ((height + TILE_H - 1) / TILE_H));
@@ -813,10 +929,11 @@ extern "C" NsbStatus nsb_unpack_tiles(NsbContext* c, const float* src_rgba, cons
 // ---- operator-level entry points -------------------------------------------------------------------------
 template <bool DENSITY_ONLY>
 static NsbStatus inference_impl(NsbContext* c, const float* coords, uint32_t n, uint16_t* out, uint32_t n_padded, void* stream) {
-	if (!c || !coords || !out) return fail(NSB_ERR_INVALID, "null argument");
+	if (!c) return fail(NSB_ERR_INVALID, "null context");
 	if (!c->has_model) return fail(NSB_ERR_STATE, "nsb_upload_model has not been called");
 	if (n_padded < n || n_padded % 128 != 0) return fail(NSB_ERR_INVALID, "n_padded must be a multiple of 128 (tcnn::batch_size_granularity) and >= n");
-	if (n_padded == 0) return NSB_OK;
+	if (n_padded == 0) return NSB_OK;  // empty batch
+	if (!coords || !out) return fail(NSB_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(c->device));
 	uint32_t grid = n_padded / 128;
 	uint32_t cap = (uint32_t)(c->sm_count * c->ctas_per_sm);

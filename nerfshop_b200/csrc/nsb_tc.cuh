@@ -54,10 +54,11 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a broken pipeline traps instead of hanging the GPU box.
+// Bounded wait: a broken pipeline traps (after ~2 s) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 	uint32_t addr = smem_u32(bar);
 	uint32_t done = 0;
+	long long t0 = 0;
 	for (uint32_t spins = 0; !done; ++spins) {
 		asm volatile(
 			"{\n\t.reg .pred p;\n\t"
@@ -66,7 +67,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 			: "=r"(done)
 			: "r"(addr), "r"(parity)
 			: "memory");
-		if (spins > (1u << 22)) __trap();
+		if (!done && (spins & 1023u) == 1023u) {
+			long long now = clock64();
+			if (t0 == 0) t0 = now;
+			else if (now - t0 > 4000000000ll) __trap();
+		}
 	}
 }
 // bulk TMA copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
@@ -148,6 +153,20 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, ui
 	umma_commit(bar);
 }
 
+// The MMA is issued by lane 0 of warp 0, but the WHOLE warp takes the branch and re-converges before anybody
+// waits on the mbarrier: if lanes 1-31 reached mbarrier.try_wait first (divergent from lane 0), the warp would
+// sleep in the hardware wait until its time-out before lane 0 ever issued the instruction it is waiting for.
+template <uint32_t N, uint32_t K>
+__device__ __forceinline__ void issue_converged(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
+	if (threadIdx.x < 32) {
+		if (threadIdx.x == 0) {
+			tc_fence_after();
+			issue_layer<N, K>(tmem_d, a_addr, w_addr, bar);
+		}
+		__syncwarp();
+	}
+}
+
 // ---- tile lifecycle -------------------------------------------------------------------------------
 // All 128 threads call; returns the TMEM base address (lane 0, column 0 of this CTA's 64 columns).
 __device__ __forceinline__ uint32_t tile_setup(TileSmem& s, const uint8_t* __restrict__ w_image) {
@@ -161,9 +180,12 @@ __device__ __forceinline__ uint32_t tile_setup(TileSmem& s, const uint8_t* __res
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
-	if (tid == 0) {
-		mbar_expect_tx(&s.w_bar, W_BYTES);
-		bulk_g2s(s.w, w_image, W_BYTES, &s.w_bar);
+	if (tid < 32) {
+		if (tid == 0) {
+			mbar_expect_tx(&s.w_bar, W_BYTES);
+			bulk_g2s(s.w, w_image, W_BYTES, &s.w_bar);
+		}
+		__syncwarp();
 	}
 	mbar_wait(&s.w_bar, 0);
 	return *reinterpret_cast<volatile uint32_t*>(&s.tmem_base);
@@ -191,14 +213,17 @@ __device__ __forceinline__ uint32_t pack(uint32_t a_bits, uint32_t b_bits) {
 // Epilogue of a 64-wide hidden layer: TMEM fp32 [row][0..63] -> ReLU -> fp16 -> a64 row (8 chunks)
 __device__ __forceinline__ void epilogue_hidden(TileSmem& s, uint32_t tmem_row, uint32_t row) {
 #pragma unroll
-	for (uint32_t q = 0; q < 4; ++q) {
-		uint32_t r[16];
-		tmem_ld16(tmem_row + q * 16, r);
+	for (uint32_t q = 0; q < 2; ++q) {
+		uint32_t r[32];
+		tmem_ld16(tmem_row + q * 32, r);
+		tmem_ld16(tmem_row + q * 32 + 16, r + 16);
 		tmem_wait_ld();
-		uint4 c0 = make_uint4(relu_pack(r[0], r[1]), relu_pack(r[2], r[3]), relu_pack(r[4], r[5]), relu_pack(r[6], r[7]));
-		uint4 c1 = make_uint4(relu_pack(r[8], r[9]), relu_pack(r[10], r[11]), relu_pack(r[12], r[13]), relu_pack(r[14], r[15]));
-		store_chunk(s.a64, 2 * q, row, c0);
-		store_chunk(s.a64, 2 * q + 1, row, c1);
+#pragma unroll
+		for (uint32_t j = 0; j < 4; ++j) {
+			uint4 c = make_uint4(relu_pack(r[8 * j + 0], r[8 * j + 1]), relu_pack(r[8 * j + 2], r[8 * j + 3]), relu_pack(r[8 * j + 4], r[8 * j + 5]),
+			                     relu_pack(r[8 * j + 6], r[8 * j + 7]));
+			store_chunk(s.a64, 4 * q + j, row, c);
+		}
 	}
 }
 
@@ -218,7 +243,7 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 	fence_async_smem();
 	tc_fence_before();
 	__syncthreads();
-	if (tid == 0) { tc_fence_after(); issue_layer<64, 32>(tmem_base, a32, w + W1_OFF, &s.mma_bar); }
+	issue_converged<64, 32>(tmem_base, a32, w + W1_OFF, &s.mma_bar);
 	mbar_wait(&s.mma_bar, phase); phase ^= 1;
 	tc_fence_after();
 	epilogue_hidden(s, tmem_row, row);
@@ -227,7 +252,7 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 	fence_async_smem();
 	tc_fence_before();
 	__syncthreads();
-	if (tid == 0) { tc_fence_after(); issue_layer<16, 64>(tmem_base, a64, w + W2_OFF, &s.mma_bar); }
+	issue_converged<16, 64>(tmem_base, a64, w + W2_OFF, &s.mma_bar);
 	mbar_wait(&s.mma_bar, phase); phase ^= 1;
 	tc_fence_after();
 	{
@@ -248,7 +273,7 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 	fence_async_smem();
 	tc_fence_before();
 	__syncthreads();
-	if (tid == 0) { tc_fence_after(); issue_layer<64, 32>(tmem_base, a32, w + W3_OFF, &s.mma_bar); }
+	issue_converged<64, 32>(tmem_base, a32, w + W3_OFF, &s.mma_bar);
 	mbar_wait(&s.mma_bar, phase); phase ^= 1;
 	tc_fence_after();
 	epilogue_hidden(s, tmem_row, row);
@@ -257,7 +282,7 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 	fence_async_smem();
 	tc_fence_before();
 	__syncthreads();
-	if (tid == 0) { tc_fence_after(); issue_layer<64, 64>(tmem_base, a64, w + W4_OFF, &s.mma_bar); }
+	issue_converged<64, 64>(tmem_base, a64, w + W4_OFF, &s.mma_bar);
 	mbar_wait(&s.mma_bar, phase); phase ^= 1;
 	tc_fence_after();
 	epilogue_hidden(s, tmem_row, row);
@@ -266,7 +291,7 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 	fence_async_smem();
 	tc_fence_before();
 	__syncthreads();
-	if (tid == 0) { tc_fence_after(); issue_layer<16, 64>(tmem_base, a64, w + W5_OFF, &s.mma_bar); }
+	issue_converged<16, 64>(tmem_base, a64, w + W5_OFF, &s.mma_bar);
 	mbar_wait(&s.mma_bar, phase); phase ^= 1;
 	tc_fence_after();
 	{

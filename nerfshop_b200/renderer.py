@@ -99,6 +99,12 @@ class NerfRenderer:
         abi.check(self.lib, self.lib.nsb_get_stats(self.ctx, C.byref(st)), "nsb_get_stats")
         return st
 
+    def debug_counters(self) -> dict:
+        out = (C.c_uint64 * 7)()
+        abi.check(self.lib, self.lib.nsb_debug_counters(self.ctx, out, 7), "nsb_debug_counters")
+        keys = ("rounds", "cyc_acquire", "cyc_encode", "cyc_mlp", "cyc_composite", "cyc_total", "ctas")
+        return dict(zip(keys, [int(v) for v in out]))
+
     # ---- multi-GPU framebuffer shards ------------------------------------------------------------------
     def tiles_for_rank(self, width, height, rank, world) -> int:
         n = C.c_uint32()
@@ -130,6 +136,9 @@ class NerfRenderer:
         c = self._coords(coords)
         n = c.shape[0]
         n_pad = ((n + 127) // 128) * 128
+        if n == 0:
+            abi.check(self.lib, fn(self.ctx, None, 0, None, 0, None), name)  # empty batch is a no-op
+            return np.zeros((rows, 0), np.uint16)
         out = torch.zeros((rows, n_pad), dtype=torch.int16, device=c.device)
         abi.check(self.lib, fn(self.ctx, c.data_ptr(), n, out.data_ptr(), n_pad, torch.cuda.current_stream().cuda_stream), name)
         torch.cuda.synchronize()
