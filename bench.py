@@ -153,7 +153,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from nerfshop_b200 import abi, synthetic as syn
+    from nerfshop_b200 import abi, parallel, synthetic as syn
     from nerfshop_b200.renderer import NerfRenderer
 
     assert torch.cuda.is_available(), "bench.py needs a GPU; there is no CPU fallback"
@@ -179,7 +179,7 @@ def main():
     host_fb = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
     host_depth = torch.zeros((H, W), dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream(dev)
-    launches_per_step = 1 + (1 + world if world > 1 else 0)
+    launches_per_step = 2 + (world if world > 1 else 0)  # k_prepare_rays + k_render_fused (+ k_pack_tiles and world-1 x unpack)
 
     def device_step(i):
         """One frame, output left in HBM (for N > 1: render own tiles, pack, all-gather, unpack every shard)."""
@@ -187,11 +187,7 @@ def main():
         fb.zero_()  # render_buffer.clear_frame
         r.render(f, fb, depth)
         if world > 1:
-            r.pack_tiles(fb, None, rank, world, shard)
-            dist.all_gather_into_tensor(gathered, shard)
-            for k in range(world):
-                if k != rank:
-                    r.unpack_tiles(gathered[k], None, k, world, fb)
+            parallel.gather_framebuffer(r, fb, rank, world, shard, gathered)
 
     def timed(step_fn, n_warm, n_steps):
         for i in range(n_warm):
