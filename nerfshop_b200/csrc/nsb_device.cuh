@@ -27,12 +27,11 @@ constexpr int TILE_PIXELS = TILE_W * TILE_H;
 struct DevLevel {
 	float scale;
 	uint32_t res;
-	uint32_t offset;  // in entries (2 x fp16 each)
-	uint32_t size;    // entries
-	uint32_t res2;    // res*res (0 when it would overflow the dense test)
+	uint32_t size;    // entries (2 x fp16 each)
+	uint32_t res2;    // res*res (0 for hashed levels)
 	uint32_t hashed;  // 1: spatial hash, 0: dense
 	uint32_t mask;    // size-1 when size is a power of two, else 0
-	uint32_t pad;
+	const __half2* base;  // first entry of the level (table + level offset): one IMAD.WIDE per gather address
 };
 
 struct DevModel {
@@ -41,6 +40,7 @@ struct DevModel {
 	const uint8_t* w_image;   // 20480-byte shared-memory image of the 5 weight matrices (UMMA B layout)
 	const __half* w_rowmajor; // the same weights, reference order (row-major per layer), for debugging kernels
 	uint32_t n_levels;
+	uint32_t pair_mode[MAX_LEVELS / 2];  // per pair of levels: 0 both dense, 1 both hashed, 2 mixed
 };
 
 struct DevFrame {
@@ -186,13 +186,13 @@ __device__ __forceinline__ float unwarp_dt(float dt) { return fma_(dt, DT_RANGE(
 __device__ __forceinline__ float calc_dt(float t, float cone) { return clampf(mul(t, cone), MIN_STEP(), MAX_STEP()); }
 
 __device__ __forceinline__ float distance_to_next_voxel(V3 pos, V3 dir, V3 idir, uint32_t res) {  // :93-101
-	float fr = (float)res;
+	float fr = (float)res;  // 128 >> mip: a power of two, so t / fr == t * (1 / fr) bit for bit
 	float px = mul(fr, pos.x), py = mul(fr, pos.y), pz = mul(fr, pos.z);
 	float tx = mul(sub(floorf(fma_(0.5f, copysignf(1.0f, dir.x), add(px, 0.5f))), px), idir.x);
 	float ty = mul(sub(floorf(fma_(0.5f, copysignf(1.0f, dir.y), add(py, 0.5f))), py), idir.y);
 	float tz = mul(sub(floorf(fma_(0.5f, copysignf(1.0f, dir.z), add(pz, 0.5f))), pz), idir.z);
 	float t = fminf(fminf(tx, ty), tz);
-	return fmaxf(div_(t, fr), 0.0f);
+	return fmaxf(mul(t, __uint_as_float(0x7f000000u - __float_as_uint(fr))), 0.0f);
 }
 __device__ __forceinline__ float advance_to_next_voxel(float t, float cone, V3 pos, V3 dir, V3 idir, uint32_t res) {  // :103-115
 	float t_target = add(t, distance_to_next_voxel(pos, dir, idir, res));
@@ -340,15 +340,20 @@ __device__ __forceinline__ MarchResult next_occupied_budget(const DevFrame& f, c
 // One level: 8 gathers of a __half2, result += (half)(weight * data) with fp16 accumulation.
 // ------------------------------------------------------------------------------------------------
 // tcnn grid_index: dense levels index x + y*res + z*res^2, the others hash the vertex (primes 1, 2654435761, 805459861).
-// Both are a handful of integer ops; the level kind is uniform across the launch, so this is a select, not a divergent branch.
+// MODE 0: dense, 1: hashed, 2: either (level kind is uniform across the launch: a select, not a divergent branch).
 template <int MODE>
 __device__ __forceinline__ uint32_t grid_index(const DevLevel& L, uint32_t gx, uint32_t gy, uint32_t gz) {
-	uint32_t h = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
-	h = L.mask ? (h & L.mask) : (h % L.size);
-	uint32_t d = gx + gy * L.res + gz * L.res2;
-	// `index % size`: a dense index is below res + res^2 + res^3 < 2*size, so one conditional subtraction is the modulo
-	d = d >= L.size ? d - L.size : d;
-	return L.hashed ? h : d;
+	uint32_t h = 0, d = 0;
+	if (MODE != 0) {
+		h = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
+		h = L.mask ? (h & L.mask) : (h % L.size);
+	}
+	if (MODE != 1) {
+		d = gx + gy * L.res + gz * L.res2;
+		// `index % size`: a dense index is below res + res^2 + res^3 < 2*size, so one conditional subtraction is the modulo
+		d = d >= L.size ? d - L.size : d;
+	}
+	return MODE == 0 ? d : (MODE == 1 ? h : (L.hashed ? h : d));
 }
 
 // NL consecutive levels at once: all 8*NL gathers are issued before the first one is consumed (memory-level parallelism;
@@ -365,7 +370,7 @@ __device__ __forceinline__ void encode_levels(const DevLevel* __restrict__ L, co
 		float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
 		wx[l] = sub(px, fx); wy[l] = sub(py, fy); wz[l] = sub(pz, fz);
 		uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-		const __half2* base = grid + L[l].offset;
+		const __half2* base = L[l].base;
 #pragma unroll
 		for (int c = 0; c < 8; ++c) v[l][c] = __ldg(base + grid_index<MODE>(L[l], gx + (c & 1), gy + ((c >> 1) & 1), gz + ((c >> 2) & 1)));
 	}

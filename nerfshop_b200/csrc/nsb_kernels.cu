@@ -101,7 +101,12 @@ __device__ __forceinline__ void encode_to_a32(tc::TileSmem& s, const DevModel& m
 	for (int g = 0; g < MAX_LEVELS / 2; ++g) {
 		__half2 h[2];
 		h[0] = h[1] = __floats2half2_rn(0.0f, 0.0f);
-		if (valid) encode_levels<2, 2>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
+		if (valid) {
+			const uint32_t mode = m.pair_mode[g];  // uniform
+			if (mode == 1) encode_levels<2, 1>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
+			else if (mode == 0) encode_levels<2, 0>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
+			else encode_levels<2, 2>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
+		}
 		// levels 2g, 2g+1 = fp16 features 4g..4g+3 = half of k-chunk g/2
 		*reinterpret_cast<uint2*>(s.a32 + (g >> 1) * (tc::ROWS * 16) + row * 16 + (g & 1) * 8) = make_uint2(tc::pack_h2(h[0]), tc::pack_h2(h[1]));
 	}
@@ -522,12 +527,11 @@ static bool build_levels(const NsbModelDesc* d, DevLevel* L, uint64_t* n_grid_en
 		n = n < (1u << d->log2_hashmap_size) ? n : (1u << d->log2_hashmap_size);
 		L[l].scale = scale;
 		L[l].res = res;
-		L[l].offset = (uint32_t)offset;
+		L[l].base = reinterpret_cast<const __half2*>((uintptr_t)offset * sizeof(__half2));  // entry offset; rebased onto the table by nsb_upload_model
 		L[l].size = n;
 		L[l].hashed = dense > (double)n ? 1u : 0u;
 		L[l].res2 = L[l].hashed ? 0u : res * res;
 		L[l].mask = (n & (n - 1)) == 0 ? n - 1 : 0u;
-		L[l].pad = 0;
 		offset += n;
 	}
 	*n_grid_entries = offset;
@@ -652,9 +656,14 @@ extern "C" NsbStatus nsb_upload_model(NsbContext* c, const NsbModelDesc* desc, c
 	CU(cudaMalloc(&c->d_grid, n_grid * 4));
 	CU(cudaMemcpy(c->d_grid, params + kMlpParams, n_grid * 4, cudaMemcpyHostToDevice));
 	m.grid = c->d_grid;
+	for (uint32_t l = 0; l < desc->n_levels; ++l) m.levels[l].base = c->d_grid + (uintptr_t)m.levels[l].base / sizeof(__half2);
 	m.w_image = c->d_wimage;
 	m.w_rowmajor = c->d_wrow;
 	m.n_levels = desc->n_levels;
+	for (int g = 0; g < MAX_LEVELS / 2; ++g) {
+		uint32_t a = m.levels[2 * g].hashed, b = m.levels[2 * g + 1].hashed;
+		m.pair_mode[g] = (a && b) ? 1u : ((!a && !b) ? 0u : 2u);
+	}
 	c->model = m;
 	c->desc = *desc;
 	c->has_model = true;

@@ -34,10 +34,15 @@ constexpr uint32_t W5_OFF = W4_OFF + 64 * 64 * 2;
 constexpr uint32_t W_BYTES = W5_OFF + 16 * 64 * 2;  // 20480
 constexpr uint32_t TMEM_COLS = 64;
 
+// The 32-wide operand (L1 / L3 input) aliases the first half of the 64-wide one (L2 / L4 / L5 input): at every point of
+// the layer chain only one of them is live (the MMA that read the other has completed before the epilogue overwrites it),
+// so a tile needs 16 KB of operand space, 36.9 KB with the weights.
 struct __align__(128) TileSmem {
 	uint8_t w[W_BYTES];
-	uint8_t a32[A32_BYTES];
-	uint8_t a64[A64_BYTES];
+	union {
+		uint8_t a64[A64_BYTES];
+		uint8_t a32[A32_BYTES];
+	};
 	uint64_t mma_bar;
 	uint64_t w_bar;
 	uint32_t tmem_base;
