@@ -39,6 +39,22 @@ BYTES_PER_SAMPLE = 512   # 16 levels x 8 corners x 2 fp16
 FLOP_PER_SAMPLE = 20480  # both MLPs
 
 
+def load_traffic():
+    """DRAM bytes per launch of k_render_fused from the committed `ncu --set full` digest (profiles/), or None."""
+    import glob
+    import re
+
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_render_fused*.txt"))):
+        txt = open(path).read()
+        rd = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        wr = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        if rd and wr:
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            best = (float(rd.group(1)) * scale.get(rd.group(2), 1.0) + float(wr.group(1)) * scale.get(wr.group(2), 1.0), os.path.basename(path))
+    return best
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -207,7 +223,7 @@ def main():
             e1.record(stream)
             evs.append((e0, e1))
             st = r.stats()  # synchronises on the render kernel's own events
-            kern_ms.append(st.gpu_ms)
+            kern_ms.append(st.fused_ms)
             samples.append(st.n_samples)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -258,6 +274,7 @@ def main():
 
     if rank == 0:
         hbm_gbs, tflops, peak_kind = load_peaks()
+        traffic = load_traffic()
         ms_per_step = total_ms / args.steps
         value = W * H / (ms_per_step * 1e-3) / 1e6
         e2e_value = W * H * args.steps / e2e_s / 1e6
@@ -275,7 +292,7 @@ def main():
                     "d2h_bytes_per_step": W * H * 20, "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"kernel": "k_render_fused", "bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                         "traffic": None, "peak_source": peak_kind, "kernel_ms": k_ms, "samples_per_launch": s_mean,
+                         "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None, "peak_source": peak_kind, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if world == 1 else None, "samples_per_launch": s_mean,
                          "tensor_tflops": s_mean * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12, "tensor_frac": s_mean * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12 / tflops},
         }
         if world == 1 and not args.no_cpu_baseline:

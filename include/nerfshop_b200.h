@@ -168,7 +168,8 @@ typedef struct {
 	uint64_t n_samples;       /* network evaluations (occupied samples composited or masked) */
 	uint64_t n_old_samples;   /* extra density evaluations for the membrane target */
 	uint32_t n_kernel_launches;
-	float    gpu_ms;          /* device time of the render kernel(s), CUDA events */
+	float    gpu_ms;          /* device time of the whole call (both kernels + counters reset), CUDA events on the launch stream */
+	float    fused_ms;        /* device time of k_render_fused alone */
 } NsbRenderStats;
 
 /* ---- lifetime -------------------------------------------------------------------- */

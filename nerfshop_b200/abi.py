@@ -84,7 +84,7 @@ class NsbEditOp(C.Structure):
 class NsbRenderStats(C.Structure):
     _fields_ = [
         ("n_rays", u64), ("n_rays_alive", u64), ("n_hit", u64), ("n_samples", u64), ("n_old_samples", u64),
-        ("n_kernel_launches", u32), ("gpu_ms", f32),
+        ("n_kernel_launches", u32), ("gpu_ms", f32), ("fused_ms", f32),
     ]
 
 

@@ -96,19 +96,27 @@ __global__ void __launch_bounds__(256) k_prepare_rays(const DevFrame f, const ui
 // Code size matters here: the fused kernel's hot loop has to live in the SM's instruction cache (profiles/README.md:
 // the first, fully unrolled version was 504 KB of SASS and stalled on instruction fetch). One loop body = 2 levels
 // (16 gathers in flight per thread), 8 iterations.
+#ifndef NSB_ENC_NL
+#define NSB_ENC_NL 2  // levels per loop iteration (8*NL gathers in flight per thread)
+#endif
 __device__ __forceinline__ void encode_to_a32(tc::TileSmem& s, const DevModel& m, bool valid, V3 pw, uint32_t row) {
+	constexpr int NL = NSB_ENC_NL;
 #pragma unroll 1
-	for (int g = 0; g < MAX_LEVELS / 2; ++g) {
-		__half2 h[2];
-		h[0] = h[1] = __floats2half2_rn(0.0f, 0.0f);
+	for (int g = 0; g < MAX_LEVELS / NL; ++g) {
+		__half2 h[NL];
+#pragma unroll
+		for (int j = 0; j < NL; ++j) h[j] = __floats2half2_rn(0.0f, 0.0f);
 		if (valid) {
-			const uint32_t mode = m.pair_mode[g];  // uniform
-			if (mode == 1) encode_levels<2, 1>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
-			else if (mode == 0) encode_levels<2, 0>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
-			else encode_levels<2, 2>(m.levels + 2 * g, m.grid, pw.x, pw.y, pw.z, h);
+			uint32_t mode = m.pair_mode[(NL * g) / 2];  // uniform
+			if (NL == 4 && m.pair_mode[(NL * g) / 2 + 1] != mode) mode = 2;
+			if (mode == 1) encode_levels<NL, 1>(m.levels + NL * g, m.grid, pw.x, pw.y, pw.z, h);
+			else if (mode == 0) encode_levels<NL, 0>(m.levels + NL * g, m.grid, pw.x, pw.y, pw.z, h);
+			else encode_levels<NL, 2>(m.levels + NL * g, m.grid, pw.x, pw.y, pw.z, h);
 		}
-		// levels 2g, 2g+1 = fp16 features 4g..4g+3 = half of k-chunk g/2
-		*reinterpret_cast<uint2*>(s.a32 + (g >> 1) * (tc::ROWS * 16) + row * 16 + (g & 1) * 8) = make_uint2(tc::pack_h2(h[0]), tc::pack_h2(h[1]));
+		// levels NL*g .. NL*g+NL-1 = fp16 features 2*NL*g ..: NL*4 bytes of this row's k-chunk (NL*g)/4
+		uint8_t* dst = s.a32 + ((NL * g) >> 2) * (tc::ROWS * 16) + row * 16 + ((NL * g) & 3) * 4;
+		if (NL == 2) *reinterpret_cast<uint2*>(dst) = make_uint2(tc::pack_h2(h[0]), tc::pack_h2(h[1]));
+		else *reinterpret_cast<uint4*>(dst) = make_uint4(tc::pack_h2(h[0]), tc::pack_h2(h[1]), tc::pack_h2(h[NL > 2 ? 2 : 0]), tc::pack_h2(h[NL > 3 ? 3 : 0]));
 	}
 }
 
@@ -500,7 +508,7 @@ struct NsbContext {
 	size_t list_capacity = 0;
 	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
 	int dda_budget = DDA_BUDGET;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;  // start, end, between k_prepare_rays and k_render_fused
 	bool timed = false;
 	uint32_t launches = 0;
 	float* d_fb = nullptr;
@@ -569,6 +577,7 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	CU(cudaMemset(c->d_stats, 0, ST_N * sizeof(unsigned long long)));
 	CU(cudaEventCreate(&c->ev0));
 	CU(cudaEventCreate(&c->ev1));
+	CU(cudaEventCreate(&c->evm));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
 	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
@@ -617,6 +626,7 @@ extern "C" NsbStatus nsb_destroy(NsbContext* c) {
 	cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_fb); cudaFree(c->d_depth); cudaFree(c->d_list);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->evm) cudaEventDestroy(c->evm);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 	return NSB_OK;
@@ -839,12 +849,14 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		c->list_capacity = n_local;
 	}
 	CU(cudaEventRecord(c->ev0, stream));
+	CU(cudaEventRecord(c->evm, stream));
 	CU(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(uint32_t), stream));
 	CU(cudaMemsetAsync(c->d_stats, 0, ST_N * sizeof(unsigned long long), stream));
 	if (n_local > 0) {
 		k_prepare_rays<<<(unsigned)((n_local + 255) / 256), 256, 0, stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, depth_dev, c->d_list, c->d_counters,
 		                                                                   (uint32_t)n_local, c->d_stats);
 		CU(cudaGetLastError());
+		CU(cudaEventRecord(c->evm, stream));
 		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
 		if (grid > my_tiles) grid = my_tiles;
 		k_render_fused<<<grid, 128, sizeof(tc::TileSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
@@ -891,6 +903,7 @@ extern "C" NsbStatus nsb_get_stats(NsbContext* c, NsbRenderStats* out) {
 	out->n_rays = h[ST_RAYS]; out->n_rays_alive = h[ST_ALIVE]; out->n_hit = h[ST_HIT]; out->n_samples = h[ST_SAMPLES]; out->n_old_samples = h[ST_OLD];
 	out->n_kernel_launches = c->launches;
 	CU(cudaEventElapsedTime(&out->gpu_ms, c->ev0, c->ev1));
+	CU(cudaEventElapsedTime(&out->fused_ms, c->evm, c->ev1));
 	return NSB_OK;
 }
 
