@@ -218,6 +218,27 @@ NsbStatus nsb_unpack_tiles(NsbContext* ctx, const float* src_packed_rgba_dev, co
                            int32_t width, int32_t height, int32_t rank, int32_t world,
                            float* fb_dev, float* depth_dev, void* stream);
 
+/* ---- frame post-process: what Testbed::render_frame runs right after render_nerf ----------------- */
+/* reference: common.h:122-135 */
+typedef enum { NSB_COLOR_LINEAR = 0, NSB_COLOR_SRGB = 1, NSB_COLOR_VISPOSNEG = 2 } NsbColorSpace;
+typedef enum { NSB_TONEMAP_IDENTITY = 0, NSB_TONEMAP_ACES = 1, NSB_TONEMAP_HABLE = 2, NSB_TONEMAP_REINHARD = 3 } NsbTonemapCurve;
+typedef struct {
+	int32_t color_space;         /* CudaRenderBuffer::m_color_space */
+	int32_t output_color_space;  /* to_srgb ? SRGB : Linear */
+	int32_t tonemap_curve;       /* m_tonemap_curve */
+	int32_t clamp_output_color;
+	float   exposure;            /* stops */
+	float   background_color[4]; /* sRGB-encoded, like the reference's m_background_color */
+} NsbTonemap;
+/* replaces CudaRenderBuffer::accumulate -> accumulate_kernel (render_buffer.cu:217-258, :540-560): running mean over spp;
+ * spp = samples already in the accumulate buffer (0: the buffer is overwritten). */
+NsbStatus nsb_accumulate(NsbContext* ctx, const float* frame_buffer_dev, float* accumulate_buffer_dev, int32_t width, int32_t height,
+                         uint32_t spp, int32_t color_space, void* stream);
+/* replaces CudaRenderBuffer::tonemap -> tonemap_kernel (render_buffer.cu:471-499, :262-332): background blend, exposure, curve,
+ * output colour space; writes float4[width*height] (the reference writes a CUDA surface of the same content). */
+NsbStatus nsb_tonemap(NsbContext* ctx, const float* accumulate_buffer_dev, float* out_rgba_dev, int32_t width, int32_t height,
+                      const NsbTonemap* params, void* stream);
+
 /* ---- operator-level entry points (unit parity; same device code as nsb_render) ------- */
 /* replaces NerfNetwork::inference_mixed_precision (testbed_nerf.cu:2892,2913):
  * coords_dev: n x 7 floats {pos3 (warped), dt, dir3 (warped)} = NerfCoordinate (nerf.h:73);

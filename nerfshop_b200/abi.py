@@ -81,6 +81,17 @@ class NsbEditOp(C.Structure):
     ]
 
 
+NSB_COLOR_LINEAR, NSB_COLOR_SRGB, NSB_COLOR_VISPOSNEG = range(3)
+NSB_TONEMAP_IDENTITY, NSB_TONEMAP_ACES, NSB_TONEMAP_HABLE, NSB_TONEMAP_REINHARD = range(4)
+
+
+class NsbTonemap(C.Structure):
+    _fields_ = [
+        ("color_space", i32), ("output_color_space", i32), ("tonemap_curve", i32), ("clamp_output_color", i32),
+        ("exposure", f32), ("background_color", f32 * 4),
+    ]
+
+
 class NsbRenderStats(C.Structure):
     _fields_ = [
         ("n_rays", u64), ("n_rays_alive", u64), ("n_hit", u64), ("n_samples", u64), ("n_old_samples", u64),
@@ -93,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "nsb_abi_version", "nsb_last_error", "nsb_create", "nsb_destroy",
     "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_set_edit_ops",
     "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
-    "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles",
+    "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_accumulate", "nsb_tonemap",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
     "nsb_build_tet_grid", "nsb_compute_mvc", "nsb_interpolate_with_mvc", "nsb_local_rotations",
 ]
@@ -135,6 +146,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_tiles_for_rank.argtypes = [i32, i32, i32, i32, C.POINTER(u32)]
     lib.nsb_pack_tiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.nsb_unpack_tiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.nsb_accumulate.argtypes = [vp, vp, vp, i32, i32, u32, i32, vp]
+    lib.nsb_tonemap.argtypes = [vp, vp, vp, i32, i32, C.POINTER(NsbTonemap), vp]
     lib.nsb_inference.argtypes = [vp, vp, u32, vp, u32, vp]
     lib.nsb_density.argtypes = [vp, vp, u32, vp, u32, vp]
     lib.nsb_encode.argtypes = [vp, vp, u32, vp, u32, vp]

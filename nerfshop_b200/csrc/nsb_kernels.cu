@@ -383,14 +383,18 @@ __global__ void __launch_bounds__(128) k_inference(const DevModel m, const float
 	tc::tile_teardown(S, tmem_base);
 }
 
-__global__ void k_encode(const DevModel m, const float* __restrict__ coords, uint32_t n, __half* __restrict__ out, uint32_t n_padded) {
+// tcnn GridEncoding inference alone: fp16 [32 x n_padded] row-major, same loop body as the fused kernel.
+__global__ void __launch_bounds__(256) k_encode(const DevModel m, const float* __restrict__ coords, uint32_t n, __half* __restrict__ out, uint32_t n_padded) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	float x = coords[7 * (size_t)i], y = coords[7 * (size_t)i + 1], z = coords[7 * (size_t)i + 2];
 #pragma unroll 1
 	for (uint32_t g = 0; g < MAX_LEVELS / 2; ++g) {
 		__half2 v[2];
-		encode_levels<2, 2>(m.levels + 2 * g, m.grid, x, y, z, v);
+		const uint32_t mode = m.pair_mode[g];  // uniform
+		if (mode == 1) encode_levels<2, 1>(m.levels + 2 * g, m.grid, x, y, z, v);
+		else if (mode == 0) encode_levels<2, 0>(m.levels + 2 * g, m.grid, x, y, z, v);
+		else encode_levels<2, 2>(m.levels + 2 * g, m.grid, x, y, z, v);
 #pragma unroll
 		for (uint32_t j = 0; j < 2; ++j) {
 			out[(size_t)(4 * g + 2 * j) * n_padded + i] = __low2half(v[j]);
@@ -449,6 +453,73 @@ __global__ void k_march_trace(const DevFrame f, const uint8_t* __restrict__ bitf
 	count[i] = c;
 }
 
+// ---- frame post-process: accumulate_kernel (render_buffer.cu:217-258) and tonemap_kernel (:471-499) -------------------
+__device__ __forceinline__ float linear_to_srgb(float l) {  // common_device.cuh:53-59
+	if (l < 0.0031308f) return 12.92f * l;
+	return 1.055f * powf(l, 0.41666f) - 0.055f;
+}
+__global__ void k_accumulate(int n, const float4* __restrict__ frame, float4* __restrict__ acc, float sample_count, int color_space) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4 c = frame[i], t = acc[i];
+	const float inv = sample_count + 1.0f;
+	if (color_space == NSB_COLOR_VISPOSNEG) {
+		float val = c.x - c.y, tmp_val = t.x - t.y;
+		tmp_val = (tmp_val * sample_count + val) / inv;
+		t.x = fmaxf(tmp_val, 0.0f);
+		t.y = fmaxf(-tmp_val, 0.0f);
+	} else {
+		if (color_space == NSB_COLOR_SRGB) { c.x = linear_to_srgb(c.x); c.y = linear_to_srgb(c.y); c.z = linear_to_srgb(c.z); }
+		t.x = (t.x * sample_count + c.x) / inv;
+		t.y = (t.y * sample_count + c.y) / inv;
+		t.z = (t.z * sample_count + c.z) / inv;
+	}
+	t.w = (t.w * sample_count + c.w) / inv;
+	acc[i] = t;
+}
+__device__ __forceinline__ void tonemap_curve(float* x, int curve) {  // render_buffer.cu:262-310
+	if (curve == NSB_TONEMAP_IDENTITY) return;
+	for (int k = 0; k < 3; ++k) x[k] = fmaxf(x[k], 0.0f);
+	float k0, k1, k2, k3, k4, k5;
+	if (curve == NSB_TONEMAP_ACES) {
+		k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+	} else if (curve == NSB_TONEMAP_HABLE) {
+		const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+		k0 = A * F - A * E; k1 = C * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+		const float W = 11.2f;
+		const float nom = k0 * (W * W) + k1 * W + k2, denom = k3 * (W * W) + k4 * W + k5;
+		const float white_scale = denom / nom;
+		k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+	} else {  // Reinhard
+		float Y = 0.2126f * x[0] + 0.7152f * x[1] + 0.0722f * x[2];
+		float s = 1.0f / (Y + 1.0f);
+		for (int k = 0; k < 3; ++k) x[k] *= s;
+		return;
+	}
+	for (int k = 0; k < 3; ++k) {
+		float sq = x[k] * x[k];
+		x[k] = (sq * k0 + k1 * x[k] + k2) / (k3 * sq + k4 * x[k] + k5);
+	}
+}
+__global__ void k_tonemap(int n, const float4* __restrict__ acc, float4* __restrict__ out, NsbTonemap p) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float bg[4] = {p.background_color[0], p.background_color[1], p.background_color[2], p.background_color[3]};
+	if (p.color_space != NSB_COLOR_SRGB) for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
+	float4 c4 = acc[i];
+	float c[3] = {c4.x, c4.y, c4.z};
+	float weight = (1.0f - c4.w) * bg[3];
+	for (int k = 0; k < 3; ++k) c[k] += bg[k] * weight;
+	float a = c4.w + weight;
+	if (p.color_space == NSB_COLOR_SRGB) for (int k = 0; k < 3; ++k) c[k] = srgb_to_linear(c[k]);
+	const float e = powf(2.0f, p.exposure);
+	for (int k = 0; k < 3; ++k) c[k] *= e;
+	tonemap_curve(c, p.tonemap_curve);
+	if (p.output_color_space == NSB_COLOR_SRGB) for (int k = 0; k < 3; ++k) c[k] = linear_to_srgb(c[k]);
+	if (p.clamp_output_color) { for (int k = 0; k < 3; ++k) c[k] = fminf(fmaxf(c[k], 0.0f), 1.0f); a = fminf(fmaxf(a, 0.0f), 1.0f); }
+	out[i] = make_float4(c[0], c[1], c[2], a);
+}
+
 // packed tile buffers for the single multi-GPU framebuffer gather
 __global__ void k_pack_tiles(const float4* __restrict__ fb, const float* __restrict__ depth, int W, int H, int tiles_x, int n_tiles, int rank, int world,
                              float4* __restrict__ dst, float* __restrict__ dst_depth, int unpack) {
@@ -491,6 +562,7 @@ struct NsbContext {
 	int device = 0;
 	int sm_count = 0;
 	int ctas_per_sm = 1;
+	int inference_ctas_per_sm = 1;
 	bool has_model = false, has_occ = false;
 	NsbModelDesc desc{};
 	DevModel model{};
@@ -598,6 +670,14 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	if (want > 8) want = 8;
 	if (want < 1) want = 1;
 	c->ctas_per_sm = want;
+	{   // the operator-level inference kernel is lighter (no ray state): its own residency
+		cudaFuncAttributes fi;
+		CU(cudaFuncGetAttributes(&fi, k_inference<false>));
+		int r = fi.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fi.numRegs * 128)) : 4;
+		c->inference_ctas_per_sm = r < by_smem ? r : by_smem;
+		if (c->inference_ctas_per_sm > 8) c->inference_ctas_per_sm = 8;
+		if (c->inference_ctas_per_sm < 1) c->inference_ctas_per_sm = 1;
+	}
 	if (const char* e = getenv("NSB_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->ctas_per_sm = v; }
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
@@ -948,6 +1028,27 @@ extern "C" NsbStatus nsb_unpack_tiles(NsbContext* c, const float* src_rgba, cons
 	return pack_impl(c, fb_dev, depth_dev, W, H, rank, world, const_cast<float*>(src_rgba), const_cast<float*>(src_depth), stream, 1);
 }
 
+extern "C" NsbStatus nsb_accumulate(NsbContext* c, const float* frame, float* acc, int32_t W, int32_t H, uint32_t spp, int32_t color_space, void* stream) {
+	if (!c || !frame || !acc || W <= 0 || H <= 0) return fail(NSB_ERR_INVALID, "bad arguments");
+	if (color_space < 0 || color_space > 2) return fail(NSB_ERR_INVALID, "bad colour space %d", color_space);
+	CU(cudaSetDevice(c->device));
+	int n = W * H;
+	if (spp == 0) CU(cudaMemsetAsync(acc, 0, (size_t)n * 16, (cudaStream_t)stream));  // render_buffer.cu:545-547
+	k_accumulate<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, reinterpret_cast<const float4*>(frame), reinterpret_cast<float4*>(acc), (float)spp, color_space);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_tonemap(NsbContext* c, const float* acc, float* out, int32_t W, int32_t H, const NsbTonemap* p, void* stream) {
+	if (!c || !acc || !out || !p || W <= 0 || H <= 0) return fail(NSB_ERR_INVALID, "bad arguments");
+	if (p->color_space < 0 || p->color_space > 2 || p->output_color_space < 0 || p->output_color_space > 1 || p->tonemap_curve < 0 || p->tonemap_curve > 3)
+		return fail(NSB_ERR_INVALID, "bad tonemap parameters");
+	CU(cudaSetDevice(c->device));
+	int n = W * H;
+	k_tonemap<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, reinterpret_cast<const float4*>(acc), reinterpret_cast<float4*>(out), *p);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+
 // ---- operator-level entry points -------------------------------------------------------------------------
 template <bool DENSITY_ONLY>
 static NsbStatus inference_impl(NsbContext* c, const float* coords, uint32_t n, uint16_t* out, uint32_t n_padded, void* stream) {
@@ -958,7 +1059,7 @@ static NsbStatus inference_impl(NsbContext* c, const float* coords, uint32_t n, 
 	if (!coords || !out) return fail(NSB_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(c->device));
 	uint32_t grid = n_padded / 128;
-	uint32_t cap = (uint32_t)(c->sm_count * c->ctas_per_sm);
+	uint32_t cap = (uint32_t)(c->sm_count * c->inference_ctas_per_sm);
 	if (grid > cap) grid = cap;
 	k_inference<DENSITY_ONLY><<<grid, 128, sizeof(tc::TileSmem), (cudaStream_t)stream>>>(c->model, coords, n, reinterpret_cast<__half*>(out), n_padded);
 	CU(cudaGetLastError());
@@ -976,7 +1077,7 @@ extern "C" NsbStatus nsb_encode(NsbContext* c, const float* coords, uint32_t n, 
 	if (n_padded < n) return fail(NSB_ERR_INVALID, "n_padded < n");
 	if (n == 0) return NSB_OK;
 	CU(cudaSetDevice(c->device));
-	k_encode<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c->model, coords, n, reinterpret_cast<__half*>(out), n_padded);
+	k_encode<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->model, coords, n, reinterpret_cast<__half*>(out), n_padded);
 	CU(cudaGetLastError());
 	return NSB_OK;
 }

@@ -125,6 +125,22 @@ class NerfRenderer:
         abi.check(self.lib, self.lib.nsb_unpack_tiles(self.ctx, packed_rgba.data_ptr(), 0 if packed_depth is None else packed_depth.data_ptr(), W, H, rank, world,
                                                       fb.data_ptr(), 0 if depth is None else depth.data_ptr(), s), "nsb_unpack_tiles")
 
+    # ---- frame post-process (CudaRenderBuffer::accumulate / ::tonemap) ---------------------------------------
+    def accumulate(self, frame_buffer, accumulate_buffer, spp: int, color_space: int = abi.NSB_COLOR_LINEAR):
+        torch = _torch()
+        H, W = frame_buffer.shape[0], frame_buffer.shape[1]
+        abi.check(self.lib, self.lib.nsb_accumulate(self.ctx, frame_buffer.data_ptr(), accumulate_buffer.data_ptr(), W, H, spp, color_space,
+                                                    torch.cuda.current_stream().cuda_stream), "nsb_accumulate")
+
+    def tonemap(self, accumulate_buffer, params: "abi.NsbTonemap", out=None):
+        torch = _torch()
+        H, W = accumulate_buffer.shape[0], accumulate_buffer.shape[1]
+        if out is None:
+            out = torch.empty_like(accumulate_buffer)
+        abi.check(self.lib, self.lib.nsb_tonemap(self.ctx, accumulate_buffer.data_ptr(), out.data_ptr(), W, H, C.byref(params),
+                                                 torch.cuda.current_stream().cuda_stream), "nsb_tonemap")
+        return out
+
     # ---- operator-level entry points ---------------------------------------------------------------------
     def _coords(self, coords):
         torch = _torch()

@@ -922,6 +922,63 @@ int orc_render(const OrcScene* s, const NsbFrame* f, float* fb, float* depth, Or
 	return 0;
 }
 
+// accumulate_kernel (render_buffer.cu:217-258) and tonemap_kernel (:471-499, curves :262-332) on host buffers
+static inline float linear_to_srgb_(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * powf(l, 0.41666f) - 0.055f; }
+int orc_accumulate(const float* frame, float* acc, int n, float sample_count, int color_space) {
+	for (int i = 0; i < n; ++i) {
+		float c[4] = {frame[4 * i], frame[4 * i + 1], frame[4 * i + 2], frame[4 * i + 3]};
+		float* t = acc + 4 * (size_t)i;
+		const float inv = sample_count + 1.0f;
+		if (color_space == NSB_COLOR_VISPOSNEG) {
+			float val = c[0] - c[1], tv = t[0] - t[1];
+			tv = (tv * sample_count + val) / inv;
+			t[0] = fmaxf(tv, 0.0f); t[1] = fmaxf(-tv, 0.0f);
+		} else {
+			if (color_space == NSB_COLOR_SRGB) for (int k = 0; k < 3; ++k) c[k] = linear_to_srgb_(c[k]);
+			for (int k = 0; k < 3; ++k) t[k] = (t[k] * sample_count + c[k]) / inv;
+		}
+		t[3] = (t[3] * sample_count + c[3]) / inv;
+	}
+	return 0;
+}
+int orc_tonemap(const float* acc, float* out, int n, const NsbTonemap* p) {
+	for (int i = 0; i < n; ++i) {
+		float bg[4] = {p->background_color[0], p->background_color[1], p->background_color[2], p->background_color[3]};
+		if (p->color_space != NSB_COLOR_SRGB) for (int k = 0; k < 3; ++k) bg[k] = srgb_to_linear(bg[k]);
+		float c[3] = {acc[4 * i], acc[4 * i + 1], acc[4 * i + 2]};
+		float a = acc[4 * i + 3];
+		float weight = (1.0f - a) * bg[3];
+		for (int k = 0; k < 3; ++k) c[k] += bg[k] * weight;
+		a += weight;
+		if (p->color_space == NSB_COLOR_SRGB) for (int k = 0; k < 3; ++k) c[k] = srgb_to_linear(c[k]);
+		const float e = powf(2.0f, p->exposure);
+		for (int k = 0; k < 3; ++k) c[k] *= e;
+		if (p->tonemap_curve != NSB_TONEMAP_IDENTITY) {
+			for (int k = 0; k < 3; ++k) c[k] = fmaxf(c[k], 0.0f);
+			if (p->tonemap_curve == NSB_TONEMAP_REINHARD) {
+				float Y = 0.2126f * c[0] + 0.7152f * c[1] + 0.0722f * c[2];
+				for (int k = 0; k < 3; ++k) c[k] *= 1.0f / (Y + 1.0f);
+			} else {
+				float k0, k1, k2, k3, k4, k5;
+				if (p->tonemap_curve == NSB_TONEMAP_ACES) {
+					k0 = 0.6f * 0.6f * 2.51f; k1 = 0.6f * 0.03f; k2 = 0.0f; k3 = 0.6f * 0.6f * 2.43f; k4 = 0.6f * 0.59f; k5 = 0.14f;
+				} else {
+					const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+					k0 = A * F - A * E; k1 = C * B * F - B * E; k2 = 0.0f; k3 = A * F; k4 = B * F; k5 = D * F * F;
+					const float W = 11.2f;
+					const float white_scale = (k3 * (W * W) + k4 * W + k5) / (k0 * (W * W) + k1 * W + k2);
+					k0 = 4.0f * k0 * white_scale; k1 = 2.0f * k1 * white_scale; k2 = k2 * white_scale; k3 = 4.0f * k3; k4 = 2.0f * k4;
+				}
+				for (int k = 0; k < 3; ++k) { float sq = c[k] * c[k]; c[k] = (sq * k0 + k1 * c[k] + k2) / (k3 * sq + k4 * c[k] + k5); }
+			}
+		}
+		if (p->output_color_space == NSB_COLOR_SRGB) for (int k = 0; k < 3; ++k) c[k] = linear_to_srgb_(c[k]);
+		if (p->clamp_output_color) { for (int k = 0; k < 3; ++k) c[k] = fminf(fmaxf(c[k], 0.0f), 1.0f); a = fminf(fmaxf(a, 0.0f), 1.0f); }
+		out[4 * i] = c[0]; out[4 * i + 1] = c[1]; out[4 * i + 2] = c[2]; out[4 * i + 3] = a;
+	}
+	return 0;
+}
+
 int orc_set_threads(int n) {
 #ifdef _OPENMP
 	if (n > 0) omp_set_num_threads(n);

@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         l.orc_march_trace.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         l.orc_render.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_void_p, C.POINTER(OrcStats), C.c_void_p]
         l.orc_set_threads.argtypes = [C.c_int]
+        l.orc_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
+        l.orc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.NsbTonemap)]
         _lib = l
     return _lib
 
@@ -148,6 +150,20 @@ class Oracle:
         rc = self.lib.orc_render(C.byref(self.scene), C.byref(frame), _ptr(fb), _ptr(depth), C.byref(stats), None if margin is None else _ptr(margin))
         assert rc == 0
         return fb, depth, stats, margin
+
+
+def accumulate(frame: np.ndarray, acc: np.ndarray, spp: int, color_space: int = 0) -> np.ndarray:
+    frame = np.ascontiguousarray(frame, np.float32)
+    acc = np.zeros_like(frame) if spp == 0 else np.ascontiguousarray(acc, np.float32).copy()
+    assert lib().orc_accumulate(_ptr(frame), _ptr(acc), frame.size // 4, float(spp), color_space) == 0
+    return acc
+
+
+def tonemap(acc: np.ndarray, params: "abi.NsbTonemap") -> np.ndarray:
+    acc = np.ascontiguousarray(acc, np.float32)
+    out = np.zeros_like(acc)
+    assert lib().orc_tonemap(_ptr(acc), _ptr(out), acc.size // 4, C.byref(params)) == 0
+    return out
 
 
 def set_threads(n: int) -> int:

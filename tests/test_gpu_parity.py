@@ -231,3 +231,35 @@ def test_no_model_is_an_error(built_lib):
     assert lib.nsb_render(ctx, C.byref(f), buf.data_ptr(), buf.data_ptr(), None) == abi.NSB_ERR_STATE
     assert b"nsb_upload_model" in lib.nsb_last_error()
     lib.nsb_destroy(ctx)
+
+
+def test_unit_cube_scene_constant_step(renderer, built_lib):
+    """aabb_scale = 1 (the reference's synthetic-Lego shape): cone angle 0 -> constant dt = sqrt(3)/1024, one cascade,
+    per_level_scale 1.3819 -> FIVE dense levels, so the level pair (4,5) is mixed dense/hashed (the generic index path)."""
+    from nerfshop_b200.renderer import NerfRenderer
+    from oracle import oracle as orc
+
+    model = syn.make_model(seed=7, aabb_scale=1)
+    occ = syn.make_occupancy(model)
+    assert abs(model.desc.per_level_scale - 1.3819) < 1e-3
+    o = orc.Oracle(model.desc, model.params, occ)
+    r = NerfRenderer(0)
+    try:
+        r.upload_model(model.desc, model.params)
+        r.upload_occupancy(occ)
+        coords = random_coords(2000, seed=21)
+        assert (r.encode(coords) == o.encode(coords)).all()
+        cam = syn.look_at((0.5, 0.6, 1.6))
+        f = syn.make_frame(model, cam, 112, 63)
+        assert f.cone_angle_constant == 0.0
+        pix = np.arange(0, 112 * 63, 3, dtype=np.uint32)
+        rec_o, idx_o, cnt_o = o.march_trace(f, pix, 256)
+        rec_g, idx_g, cnt_g = r.march_trace(f, pix, 256)
+        assert (cnt_o == cnt_g).all() and (idx_o == idx_g).all() and (rec_o.view(np.uint32) == rec_g.view(np.uint32)).all()
+        assert cnt_o.max() > 20 and (idx_o[..., 0] == 0).all()  # a single cascade
+        fb_o, depth_o, st_o, margin = o.render(f, want_margin=True)
+        fb, depth = r.render(f)
+        _compare_frames(fb.cpu().numpy(), depth.cpu().numpy(), fb_o, depth_o, margin)
+        assert r.stats().n_samples == st_o.n_samples
+    finally:
+        r.close()
