@@ -187,6 +187,11 @@ NsbStatus nsb_model_n_params(const NsbModelDesc* desc, uint64_t* n_params);
 NsbStatus nsb_upload_model(NsbContext* ctx, const NsbModelDesc* desc, const uint16_t* params_fp16, uint64_t n_params);
 /* replaces Testbed::Nerf::density_grid_bitfield (testbed.h:626; built at testbed.cu:3079). */
 NsbStatus nsb_upload_occupancy(NsbContext* ctx, const uint8_t* bitfield, uint64_t n_bytes);
+/* replaces Testbed::update_density_grid_mean_and_bitfield (testbed_nerf.cu:3642-3658: mean of cascade 0, grid_to_bitfield :514,
+ * bitfield_max_pool :534), the step load_snapshot runs on the float density grid of a snapshot (testbed.cu:3078-3079):
+ * density_grid: HOST float[5*128^3]; the resulting bitfield becomes the context's occupancy and, if bitfield_out != NULL,
+ * is also copied back (NSB_BITFIELD_BYTES). */
+NsbStatus nsb_upload_density_grid(NsbContext* ctx, const float* density_grid, uint64_t n_floats, uint8_t* bitfield_out);
 /* replaces NerfTracer::{add,delete,reset}_edit_operator; list order = m_edit_operators order
  * (operators are applied in REVERSE list order, testbed_nerf.cu:2868,2899). n = 0 clears. */
 NsbStatus nsb_set_edit_ops(NsbContext* ctx, const NsbEditOp* ops, int32_t n);

@@ -102,7 +102,7 @@ class NsbRenderStats(C.Structure):
 # every symbol include/nerfshop_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "nsb_abi_version", "nsb_last_error", "nsb_create", "nsb_destroy",
-    "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_set_edit_ops",
+    "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_upload_density_grid", "nsb_set_edit_ops",
     "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
     "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_accumulate", "nsb_tonemap",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
@@ -138,6 +138,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_model_n_params.argtypes = [C.POINTER(NsbModelDesc), C.POINTER(u64)]
     lib.nsb_upload_model.argtypes = [vp, C.POINTER(NsbModelDesc), vp, u64]
     lib.nsb_upload_occupancy.argtypes = [vp, vp, u64]
+    lib.nsb_upload_density_grid.argtypes = [vp, vp, u64, vp]
     lib.nsb_set_edit_ops.argtypes = [vp, C.POINTER(NsbEditOp), i32]
     lib.nsb_render.argtypes = [vp, C.POINTER(NsbFrame), vp, vp, vp]
     lib.nsb_render_host.argtypes = [vp, C.POINTER(NsbFrame), vp, vp]

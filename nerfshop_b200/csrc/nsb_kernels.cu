@@ -453,6 +453,44 @@ __global__ void k_march_trace(const DevFrame f, const uint8_t* __restrict__ bitf
 	count[i] = c;
 }
 
+// ---- density grid -> occupancy bitfield (testbed_nerf.cu:514-555, :3642-3658) -----------------------------------------
+__global__ void k_grid_mean_partial(const float* __restrict__ grid, uint32_t n, double* __restrict__ partial) {
+	// fixed-shape tree: 256 threads x 64 values each per block, pairwise in shared memory (deterministic order)
+	__shared__ double sh[256];
+	uint32_t base = blockIdx.x * 256u * 64u + threadIdx.x * 64u;
+	double acc = 0.0;
+	for (uint32_t k = 0; k < 64; ++k) { uint32_t i = base + k; if (i < n) acc += (double)fmaxf(grid[i], 0.0f); }
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
+	if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void k_grid_to_bitfield(uint32_t n_bytes, const float* __restrict__ grid, uint8_t* __restrict__ bits, float thresh) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_bytes) return;
+	uint8_t b = 0;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) b |= grid[(size_t)i * 8 + j] > thresh ? (uint8_t)(1u << j) : (uint8_t)0;
+	bits[i] = b;
+}
+__device__ __forceinline__ uint32_t morton3D_invert(uint32_t x) {
+	x = x & 0x49249249u;
+	x = (x | (x >> 2)) & 0xc30c30c3u;
+	x = (x | (x >> 4)) & 0x0f00f00fu;
+	x = (x | (x >> 8)) & 0xff0000ffu;
+	x = (x | (x >> 16)) & 0x0000ffffu;
+	return x;
+}
+__global__ void k_bitfield_max_pool(uint32_t n, const uint8_t* __restrict__ prev_level, uint8_t* __restrict__ next_level) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint8_t b = 0;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) b |= prev_level[(size_t)i * 8 + j] > 0 ? (uint8_t)(1u << j) : (uint8_t)0;
+	uint32_t x = morton3D_invert(i >> 0) + GRIDSIZE / 8, y = morton3D_invert(i >> 1) + GRIDSIZE / 8, z = morton3D_invert(i >> 2) + GRIDSIZE / 8;
+	next_level[morton3D(x, y, z)] |= b;
+}
+
 // ---- frame post-process: accumulate_kernel (render_buffer.cu:217-258) and tonemap_kernel (:471-499) -------------------
 __device__ __forceinline__ float linear_to_srgb(float l) {  // common_device.cuh:53-59
 	if (l < 0.0031308f) return 12.92f * l;
@@ -767,6 +805,39 @@ extern "C" NsbStatus nsb_upload_occupancy(NsbContext* c, const uint8_t* bitfield
 	if (!c->d_bitfield) CU(cudaMalloc(&c->d_bitfield, NSB_BITFIELD_BYTES));
 	CU(cudaDeviceSynchronize());
 	CU(cudaMemcpy(c->d_bitfield, bitfield, NSB_BITFIELD_BYTES, cudaMemcpyHostToDevice));
+	c->has_occ = true;
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_upload_density_grid(NsbContext* c, const float* grid, uint64_t n_floats, uint8_t* bitfield_out) {
+	if (!c || !grid) return fail(NSB_ERR_INVALID, "null argument");
+	if (n_floats != (uint64_t)NSB_GRID_CELLS) return fail(NSB_ERR_INVALID, "density grid must be 5 x 128^3 floats");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	float* d_grid = nullptr;
+	double* d_partial = nullptr;
+	CU(cudaMalloc(&d_grid, n_floats * 4));
+	CU(cudaMemcpy(d_grid, grid, n_floats * 4, cudaMemcpyHostToDevice));
+	const uint32_t n0 = GRIDVOL, n_blocks = (n0 + 256 * 64 - 1) / (256 * 64);
+	CU(cudaMalloc(&d_partial, n_blocks * sizeof(double)));
+	k_grid_mean_partial<<<n_blocks, 256>>>(d_grid, n0, d_partial);
+	std::vector<double> partial(n_blocks);
+	CU(cudaMemcpy(partial.data(), d_partial, n_blocks * sizeof(double), cudaMemcpyDeviceToHost));
+	double sum = 0.0;
+	for (double p : partial) sum += p;
+	const float mean = (float)(sum / (double)n0);               // reduce_sum(fmaxf(val,0)/n) over cascade 0 (:3650)
+	const float thresh = mean < 0.01f ? mean : 0.01f;            // std::min(NERF_MIN_OPTICAL_THICKNESS(), mean) (:524)
+	if (!c->d_bitfield) CU(cudaMalloc(&c->d_bitfield, NSB_BITFIELD_BYTES));
+	k_grid_to_bitfield<<<(NSB_BITFIELD_BYTES + 255) / 256, 256>>>(NSB_BITFIELD_BYTES, d_grid, c->d_bitfield, thresh);
+	for (uint32_t level = 1; level < NSB_NERF_CASCADES; ++level) {
+		const uint32_t n = GRIDVOL / 64;
+		k_bitfield_max_pool<<<(n + 255) / 256, 256>>>(n, c->d_bitfield + (size_t)(level - 1) * (GRIDVOL / 8), c->d_bitfield + (size_t)level * (GRIDVOL / 8));
+	}
+	CU(cudaGetLastError());
+	CU(cudaDeviceSynchronize());
+	if (bitfield_out) CU(cudaMemcpy(bitfield_out, c->d_bitfield, NSB_BITFIELD_BYTES, cudaMemcpyDeviceToHost));
+	cudaFree(d_grid);
+	cudaFree(d_partial);
 	c->has_occ = true;
 	return NSB_OK;
 }

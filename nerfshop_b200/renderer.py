@@ -55,6 +55,13 @@ class NerfRenderer:
         b = np.ascontiguousarray(bitfield, dtype=np.uint8)
         abi.check(self.lib, self.lib.nsb_upload_occupancy(self.ctx, b.ctypes.data, b.size), "nsb_upload_occupancy")
 
+    def upload_density_grid(self, density_grid: np.ndarray) -> np.ndarray:
+        """Snapshot path: float[5*128^3] density grid -> occupancy bitfield (returned) — update_density_grid_mean_and_bitfield."""
+        g = np.ascontiguousarray(density_grid, dtype=np.float32).reshape(-1)
+        out = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8)
+        abi.check(self.lib, self.lib.nsb_upload_density_grid(self.ctx, g.ctypes.data, g.size, out.ctypes.data), "nsb_upload_density_grid")
+        return out
+
     def set_edit_operators(self, ops):
         """ops: list of (NsbEditOp, keepalive) in m_edit_operators order."""
         self._ops = list(ops or [])

@@ -979,6 +979,39 @@ int orc_tonemap(const float* acc, float* out, int n, const NsbTonemap* p) {
 	return 0;
 }
 
+// update_density_grid_mean_and_bitfield (testbed_nerf.cu:3642-3658) + grid_to_bitfield (:514) + bitfield_max_pool (:534)
+static inline uint32_t morton3D_invert_(uint32_t x) {
+	x = x & 0x49249249u;
+	x = (x | (x >> 2)) & 0xc30c30c3u;
+	x = (x | (x >> 4)) & 0x0f00f00fu;
+	x = (x | (x >> 8)) & 0xff0000ffu;
+	x = (x | (x >> 16)) & 0x0000ffffu;
+	return x;
+}
+int orc_density_grid_to_bitfield(const float* grid /*5*128^3*/, uint8_t* bits /*5*128^3/8*/, float* mean_out) {
+	double sum = 0.0;
+	for (uint32_t i = 0; i < GRIDVOL; ++i) sum += (double)fmaxf(grid[i], 0.0f);
+	float mean = (float)(sum / (double)GRIDVOL);
+	float thresh = std::min(0.01f, mean);
+	for (uint32_t i = 0; i < GRIDVOL / 8 * (uint32_t)CASCADES; ++i) {
+		uint8_t b = 0;
+		for (int j = 0; j < 8; ++j) b |= grid[(size_t)i * 8 + j] > thresh ? (uint8_t)(1u << j) : (uint8_t)0;
+		bits[i] = b;
+	}
+	for (int level = 1; level < CASCADES; ++level) {
+		const uint8_t* prev = bits + (size_t)(level - 1) * (GRIDVOL / 8);
+		uint8_t* next = bits + (size_t)level * (GRIDVOL / 8);
+		for (uint32_t i = 0; i < GRIDVOL / 64; ++i) {
+			uint8_t b = 0;
+			for (int j = 0; j < 8; ++j) b |= prev[(size_t)i * 8 + j] > 0 ? (uint8_t)(1u << j) : (uint8_t)0;
+			uint32_t x = morton3D_invert_(i >> 0) + GRIDSIZE / 8, y = morton3D_invert_(i >> 1) + GRIDSIZE / 8, z = morton3D_invert_(i >> 2) + GRIDSIZE / 8;
+			next[morton3D(x, y, z)] |= b;
+		}
+	}
+	if (mean_out) *mean_out = mean;
+	return 0;
+}
+
 int orc_set_threads(int n) {
 #ifdef _OPENMP
 	if (n > 0) omp_set_num_threads(n);

@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
         l.orc_march_trace.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         l.orc_render.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_void_p, C.POINTER(OrcStats), C.c_void_p]
         l.orc_set_threads.argtypes = [C.c_int]
+        l.orc_density_grid_to_bitfield.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         l.orc_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         l.orc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.NsbTonemap)]
         _lib = l
@@ -164,6 +165,14 @@ def tonemap(acc: np.ndarray, params: "abi.NsbTonemap") -> np.ndarray:
     out = np.zeros_like(acc)
     assert lib().orc_tonemap(_ptr(acc), _ptr(out), acc.size // 4, C.byref(params)) == 0
     return out
+
+
+def density_grid_to_bitfield(grid: np.ndarray):
+    grid = np.ascontiguousarray(grid, np.float32).reshape(-1)
+    bits = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8)
+    mean = C.c_float()
+    assert lib().orc_density_grid_to_bitfield(_ptr(grid), _ptr(bits), C.byref(mean)) == 0
+    return bits, mean.value
 
 
 def set_threads(n: int) -> int:
