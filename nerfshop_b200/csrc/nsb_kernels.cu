@@ -127,13 +127,22 @@ __device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__u
 // ONE sample; samples go deform -> hash encode -> tcgen05 MLPs -> composite inside the SM; a finished ray is shaded
 // into the framebuffer and its slot refilled from the queue (warp-aggregated fetch, so rays that were refilled
 // together — neighbouring pixels that die on the same surface — stay together in a warp).
+// Per-slot ray state parked in shared memory (SoA: lane-contiguous, conflict-free). Only the acquire and composite phases
+// touch it, so it does not occupy registers while the thread gathers hash-grid features and walks the MLP layers.
+enum { R_OX = 0, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_T, R_CR, R_CG, R_CB, R_CA, R_DEPTH, R_MAXW, R_FIELDS };
+struct RenderSmem {
+	tc::TileSmem tile;
+	float ray[R_FIELDS][128];
+};
+
 __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
                                                       float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
                                                       const uint32_t* __restrict__ n_queued_ptr, uint32_t* fetch_counter,
                                                       unsigned long long* __restrict__ stats, const int refill_thr, const int dda_budget) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
-	tc::TileSmem& S = *reinterpret_cast<tc::TileSmem*>(smem_raw);
+	RenderSmem& RS = *reinterpret_cast<RenderSmem*>(smem_raw);
+	tc::TileSmem& S = RS.tile;
 	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u;
 	const uint32_t n_queued = *n_queued_ptr;
@@ -142,24 +151,18 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 	const uint32_t tmem_base = tc::tile_setup(S, m.w_image);
 
 	const bool ops_on = f.apply_ops && n_ops > 0;
-	const float sat = 1.0f - f.min_T;  // rendering_min_transmittance test of composite_kernel_nerf :951
-	const V3 cam_fwd = v3(f.cam1[6], f.cam1[7], f.cam1[8]);
-	const V3 cam_org = v3(f.cam1[9], f.cam1[10], f.cam1[11]);
 
-	// ray state (registers)
+	// what stays in registers across a round
 	bool alive = false, exhausted = false;
-	V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), idir = v3(0, 0, 0);
-	float t = 0.0f;
-	float cr = 0, cg = 0, cb = 0, ca = 0, ray_depth = 0, max_weight = 0;
 	uint32_t pix = 0, n_steps = 0;
-	unsigned long long c_hit = 0, c_samples = 0, c_old = 0;
+	uint32_t c_hit = 0, c_samples = 0, c_old = 0;
 	uint32_t phase = 0;
 	// phase profile (thread 0 of each CTA; a handful of clock reads per round)
 	long long cyc_acq = 0, cyc_enc = 0, cyc_mlp = 0, cyc_comp = 0, n_rounds = 0;
 	const long long cyc_start = clock64();
 
 	// shade_kernel_nerf (:2464-2482) for the ray this thread just finished (compact_kernel_nerf :2503 filter)
-	auto finish = [&](bool left_aabb) {
+	auto finish = [&](bool left_aabb, float cr, float cg, float cb, float ca, float ray_depth) {
 		alive = false;
 		if (!(ca > 0.001f)) return;
 		++c_hit;
@@ -183,43 +186,59 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 		// ---- acquire one occupied sample for this thread (refill the ray slot when it is free) ----
 		bool has_sample = false;
 		float dt = 0.0f;
-		V3 pos = v3(0, 0, 0);
-		int budget = dda_budget;
-		// Coherent refill: free lanes wait until the warp is down to <= refill_thr live rays and then refill TOGETHER
-		// with consecutive queue entries (= neighbouring pixels), so the lanes of a warp gather from the same few
-		// hash-grid cells on the coarse and middle levels instead of 32 unrelated cache lines per instruction.
-		const bool may_refill = __popc(__ballot_sync(0xffffffffu, alive)) <= refill_thr;
-		for (;;) {
-			if (!alive) {
-				if (exhausted || !may_refill) break;
-				// warp-aggregated fetch: the lanes that need a ray right now take consecutive queue entries
-				const unsigned grp = __activemask();
-				const int leader = __ffs(grp) - 1;
-				uint32_t base = 0;
-				if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(grp));
-				base = __shfl_sync(grp, base, leader);
-				const uint32_t qi = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-				if (qi >= n_queued) { exhausted = true; break; }
-				const RayRec rr = list[qi];
-				pix = rr.pix;
-				Ray r;
-				make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
-				ro = r.o; rd = r.d;
-				idir = v3(div_(1.0f, rd.x), div_(1.0f, rd.y), div_(1.0f, rd.z));
-				t = rr.t;
-				cr = cg = cb = ca = 0.0f;
-				ray_depth = 0.0f; max_weight = 0.0f; n_steps = 0;
-				alive = true;
+		V3 pos = v3(0, 0, 0), dw = v3(0.5f, 0.5f, 0.5f);
+		{
+			int budget = dda_budget;
+			V3 ro = v3(RS.ray[R_OX][tid], RS.ray[R_OY][tid], RS.ray[R_OZ][tid]);
+			V3 rd = v3(RS.ray[R_DX][tid], RS.ray[R_DY][tid], RS.ray[R_DZ][tid]);
+			float t = RS.ray[R_T][tid];
+			// Coherent refill: free lanes wait until the warp is down to <= refill_thr live rays and then refill TOGETHER
+			// with consecutive queue entries (= neighbouring pixels), so the lanes of a warp gather from the same few
+			// hash-grid cells on the coarse and middle levels instead of 32 unrelated cache lines per instruction.
+			const bool may_refill = __popc(__ballot_sync(0xffffffffu, alive)) <= refill_thr;
+			for (;;) {
+				if (!alive) {
+					if (exhausted || !may_refill) break;
+					// warp-aggregated fetch: the lanes that need a ray right now take consecutive queue entries
+					const unsigned grp = __activemask();
+					const int leader = __ffs(grp) - 1;
+					uint32_t base = 0;
+					if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(grp));
+					base = __shfl_sync(grp, base, leader);
+					const uint32_t qi = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+					if (qi >= n_queued) { exhausted = true; break; }
+					const RayRec rr = list[qi];
+					pix = rr.pix;
+					Ray r;
+					make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
+					ro = r.o; rd = r.d;
+					t = rr.t;
+					RS.ray[R_OX][tid] = ro.x; RS.ray[R_OY][tid] = ro.y; RS.ray[R_OZ][tid] = ro.z;
+					RS.ray[R_DX][tid] = rd.x; RS.ray[R_DY][tid] = rd.y; RS.ray[R_DZ][tid] = rd.z;
+					RS.ray[R_CR][tid] = 0.0f; RS.ray[R_CG][tid] = 0.0f; RS.ray[R_CB][tid] = 0.0f; RS.ray[R_CA][tid] = 0.0f;
+					RS.ray[R_DEPTH][tid] = 0.0f; RS.ray[R_MAXW][tid] = 0.0f;
+					n_steps = 0;
+					alive = true;
+				}
+				if (n_steps >= MARCH_ITER - 1) { alive = false; continue; }  // still marching after MARCH_ITER steps: dropped (:2812)
+				const V3 idir = v3(div_(1.0f, rd.x), div_(1.0f, rd.y), div_(1.0f, rd.z));
+				const MarchResult mr = next_occupied_budget(f, bitfield, ro, rd, idir, t, dt, pos, budget);
+				if (mr == MARCH_FOUND) { has_sample = true; break; }
+				if (mr == MARCH_EXIT) {
+					finish(true, RS.ray[R_CR][tid], RS.ray[R_CG][tid], RS.ray[R_CB][tid], RS.ray[R_CA][tid], RS.ray[R_DEPTH][tid]);
+					continue;
+				}
+				break;  // MARCH_PENDING: resume next round
 			}
-			if (n_steps >= MARCH_ITER - 1) { alive = false; continue; }  // still marching after MARCH_ITER steps: dropped (:2812)
-			const MarchResult mr = next_occupied_budget(f, bitfield, ro, rd, idir, t, dt, pos, budget);
-			if (mr == MARCH_FOUND) { has_sample = true; break; }
-			if (mr == MARCH_EXIT) { finish(true); continue; }
-			break;  // MARCH_PENDING: resume next round
+			if (has_sample) {
+				dw = warp_direction(rd);
+				t = add(t, dt);
+			}
+			if (alive) RS.ray[R_T][tid] = t;
 		}
 
 		// ---- network inputs: generate_next_nerf_network_inputs :690 ----
-		V3 pw = v3(0, 0, 0), dw = v3(0.5f, 0.5f, 0.5f);
+		V3 pw = v3(0, 0, 0);
 		float dtw = 0.0f;
 		bool empty = false;
 		Membrane mem;
@@ -228,9 +247,7 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 		V3 pw_old = pw;
 		if (has_sample) {
 			pw = warp_position(pos, f.tmin, f.tmax);
-			dw = warp_direction(rd);
 			dtw = warp_dt(dt);
-			t = add(t, dt);
 			++n_steps;
 			++c_samples;
 			if (ops_on) {
@@ -248,8 +265,6 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 		// evaluated only in rounds where some lane needs it, density MLP only. Pass 1 is the real sample. One code copy.
 		float sigma_old_raw = 0.0f;
 		uint32_t dens[8], rgbo[8];
-		__half2 sh[8];
-		encode_sh4(dw, sh);
 		int first_pass = 1;
 		if (ops_on && any_poisson && f.poisson_target) first_pass = __syncthreads_or(need_old ? 1 : 0) ? 0 : 1;
 		const long long c1 = clock64();
@@ -260,7 +275,7 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 			const long long e0 = clock64();
 			encode_to_a32(S, m, old_pass ? need_old : has_sample, old_pass ? pw_old : pw, tid);
 			enc_cycles += clock64() - e0;
-			tc::run_network(S, tmem_base, phase, sh, old_pass, dens, rgbo);
+			tc::run_network(S, tmem_base, phase, dw, old_pass, dens, rgbo);
 			if (old_pass) {
 				sigma_old_raw = h_lo(dens[0]);
 				if (need_old) ++c_old;
@@ -271,6 +286,10 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 
 		// ---- composite_kernel_nerf :750-955 for this one sample ----
 		if (has_sample) {
+			const float sat = 1.0f - f.min_T;  // rendering_min_transmittance test of composite_kernel_nerf :951
+			const V3 cam_fwd = v3(f.cam1[6], f.cam1[7], f.cam1[8]);
+			float cr = RS.ray[R_CR][tid], cg = RS.ray[R_CG][tid], cb = RS.ray[R_CB][tid], ca = RS.ray[R_CA][tid];
+			float ray_depth = RS.ray[R_DEPTH][tid], max_weight = RS.ray[R_MAXW][tid];
 			V3 cpos = unwarp_position(pw, f.tmin, f.tmax);
 			float T = 1.0f - ca;
 			float dtu = unwarp_dt(dtw);
@@ -293,11 +312,14 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 			}
 			float weight = alpha * T;
 			float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
-			if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
-			else if (f.mode == NSB_RENDER_POSITIONS) { rgb[0] = (cpos.x - 0.5f) / 2.0f + 0.5f; rgb[1] = (cpos.y - 0.5f) / 2.0f + 0.5f; rgb[2] = (cpos.z - 0.5f) / 2.0f + 0.5f; }
-			else if (f.mode == NSB_RENDER_DEPTH) { float z = dot3(cam_fwd, vsub(cpos, ro)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
-			else if (f.mode == NSB_RENDER_DISTANCE) { V3 q = vsub(cpos, ro); float z = sqrtf(dot3(q, q)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
-			else if (f.mode == NSB_RENDER_STEPSIZE) { float wdt = warp_dt(dtu); rgb[0] = rgb[1] = rgb[2] = wdt; }
+			if (f.mode != NSB_RENDER_SHADE) {
+				const V3 ro = v3(RS.ray[R_OX][tid], RS.ray[R_OY][tid], RS.ray[R_OZ][tid]);
+				if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
+				else if (f.mode == NSB_RENDER_POSITIONS) { rgb[0] = (cpos.x - 0.5f) / 2.0f + 0.5f; rgb[1] = (cpos.y - 0.5f) / 2.0f + 0.5f; rgb[2] = (cpos.z - 0.5f) / 2.0f + 0.5f; }
+				else if (f.mode == NSB_RENDER_DEPTH) { float z = dot3(cam_fwd, vsub(cpos, ro)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
+				else if (f.mode == NSB_RENDER_DISTANCE) { V3 q = vsub(cpos, ro); float z = sqrtf(dot3(q, q)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
+				else if (f.mode == NSB_RENDER_STEPSIZE) { float wdt = warp_dt(dtu); rgb[0] = rgb[1] = rgb[2] = wdt; }
+			}
 			if (membrane) {
 				float alpha_N = 1.0f - __expf(-sigma * dtu);
 				float alpha_R = 1.0f - __expf(-mem.dob * dtu);
@@ -313,11 +335,17 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 				cb = __fmaf_rn(rgb[2], weight, cb);
 			}
 			ca += weight;
-			if (weight > max_weight) { max_weight = weight; ray_depth = dot3(cam_fwd, vsub(cpos, cam_org)); }
+			if (weight > max_weight) {
+				max_weight = weight;
+				ray_depth = dot3(cam_fwd, vsub(cpos, v3(f.cam1[9], f.cam1[10], f.cam1[11])));
+			}
 			if (ca > sat) {
 				float a = ca;
 				cr = __fdiv_rn(cr, a); cg = __fdiv_rn(cg, a); cb = __fdiv_rn(cb, a); ca = __fdiv_rn(ca, a);
-				finish(false);
+				finish(false, cr, cg, cb, ca, ray_depth);
+			} else {
+				RS.ray[R_CR][tid] = cr; RS.ray[R_CG][tid] = cg; RS.ray[R_CB][tid] = cb; RS.ray[R_CA][tid] = ca;
+				RS.ray[R_DEPTH][tid] = ray_depth; RS.ray[R_MAXW][tid] = max_weight;
 			}
 		}
 		cyc_acq += c1 - c0; cyc_enc += c2 - c1; cyc_mlp += c3 - c2; cyc_comp += clock64() - c3; ++n_rounds;
@@ -335,7 +363,7 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 	}
 
 	// counters: warp reduce, one atomic per warp
-	unsigned long long c[3] = {c_hit, c_samples, c_old};
+	unsigned long long c[3] = {c_hit, c_samples, c_old};  // per-thread counts fit 32 bits (one thread composites < 2^32 samples per frame)
 	const int slot[3] = {ST_HIT, ST_SAMPLES, ST_OLD};
 #pragma unroll
 	for (int k = 0; k < 3; ++k) {
@@ -366,10 +394,8 @@ __global__ void __launch_bounds__(128) k_inference(const DevModel m, const float
 			dw = v3(coords[7 * (size_t)i + 4], coords[7 * (size_t)i + 5], coords[7 * (size_t)i + 6]);
 		}
 		uint32_t dens[8], rgbo[8];
-		__half2 sh[8];
 		encode_to_a32(S, m, valid, pw, tid);
-		encode_sh4(dw, sh);
-		tc::run_network(S, tmem_base, phase, sh, DENSITY_ONLY, dens, rgbo);
+		tc::run_network(S, tmem_base, phase, dw, DENSITY_ONLY, dens, rgbo);
 		if (i < n_padded) {
 			const uint32_t* src = DENSITY_ONLY ? dens : rgbo;
 #pragma unroll
@@ -689,7 +715,7 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	CU(cudaEventCreate(&c->ev1));
 	CU(cudaEventCreate(&c->evm));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
+	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RenderSmem)));
 	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
 	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
 	// Persistent grid = SMs x resident CTAs. Residency is bounded by registers (128/thread -> 4), shared memory
@@ -699,11 +725,12 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	int occ = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_fused, 128, sizeof(tc::TileSmem)));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_fused, 128, sizeof(RenderSmem)));
 	cudaFuncAttributes fa;
 	CU(cudaFuncGetAttributes(&fa, k_render_fused));
 	int by_regs = fa.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fa.numRegs * 128)) : 4;
-	int by_smem = (int)(prop.sharedMemPerMultiprocessor / (sizeof(tc::TileSmem) + 1024));
+	int by_smem = (int)(prop.sharedMemPerMultiprocessor / (sizeof(RenderSmem) + 1024));
+	const int by_smem_tile = (int)(prop.sharedMemPerMultiprocessor / (sizeof(tc::TileSmem) + 1024));
 	int want = by_regs < by_smem ? by_regs : by_smem;
 	if (want > 8) want = 8;
 	if (want < 1) want = 1;
@@ -712,7 +739,7 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 		cudaFuncAttributes fi;
 		CU(cudaFuncGetAttributes(&fi, k_inference<false>));
 		int r = fi.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fi.numRegs * 128)) : 4;
-		c->inference_ctas_per_sm = r < by_smem ? r : by_smem;
+		c->inference_ctas_per_sm = r < by_smem_tile ? r : by_smem_tile;
 		if (c->inference_ctas_per_sm > 8) c->inference_ctas_per_sm = 8;
 		if (c->inference_ctas_per_sm < 1) c->inference_ctas_per_sm = 1;
 	}
@@ -721,7 +748,7 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
 	if (getenv("NSB_VERBOSE"))
 		fprintf(stderr, "[nsb] device %d: %d SMs, occupancy API %d, regs %d -> %d, smem %zu -> %d, using %d CTAs/SM\n", device, c->sm_count, occ, fa.numRegs, by_regs,
-		        sizeof(tc::TileSmem), by_smem, c->ctas_per_sm);
+		        sizeof(RenderSmem), by_smem, c->ctas_per_sm);
 	*out = c;
 	return NSB_OK;
 }
@@ -1010,7 +1037,7 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		CU(cudaEventRecord(c->evm, stream));
 		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
 		if (grid > my_tiles) grid = my_tiles;
-		k_render_fused<<<grid, 128, sizeof(tc::TileSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
+		k_render_fused<<<grid, 128, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
 		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
 		                                                          c->refill_thr, c->dda_budget);
 		CU(cudaGetLastError());

@@ -19,6 +19,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include "nsb_device.cuh"
+
 namespace nsb {
 namespace tc {
 
@@ -235,9 +237,9 @@ __device__ __forceinline__ void epilogue_hidden(TileSmem& s, uint32_t tmem_row, 
 // Runs the network on the 128 rows whose grid features are already in s.a32 (chunks 0-3).
 //   density_only: stop after L2 (NerfNetwork::density)
 //   dens[8]: the 16 fp16 outputs of the density MLP (packed half2), rgb[8]: the 16 outputs of the rgb MLP.
-// `sh` = this row's 16 SH values (8 half2), consumed between L2 and L3.
+// `dw` = this row's warped view direction; its 16 SH values are evaluated between L2 and L3.
 // `phase` is the running parity of s.mma_bar (one flip per layer).
-__device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uint32_t& phase, const __half2* sh, bool density_only,
+__device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uint32_t& phase, V3 dw, bool density_only,
                                             uint32_t* dens, uint32_t* rgb) {
 	const uint32_t tid = threadIdx.x;
 	const uint32_t row = tid;
@@ -269,6 +271,8 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 	}
 	if (density_only) { tc_fence_before(); return; }
 	// rgb-network input: rows 0-15 = density MLP output, 16-31 = SH (nerf_network_full.h:52,67,79)
+	__half2 sh[8];
+	encode_sh4(dw, sh);  // tcnn SphericalHarmonics of the (mapped) direction: rows 16-31 of the rgb network input
 	store_chunk(s.a32, 0, row, make_uint4(dens[0], dens[1], dens[2], dens[3]));
 	store_chunk(s.a32, 1, row, make_uint4(dens[4], dens[5], dens[6], dens[7]));
 	store_chunk(s.a32, 2, row, make_uint4(pack_h2(sh[0]), pack_h2(sh[1]), pack_h2(sh[2]), pack_h2(sh[3])));
