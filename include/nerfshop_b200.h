@@ -244,6 +244,32 @@ NsbStatus nsb_accumulate(NsbContext* ctx, const float* frame_buffer_dev, float* 
 NsbStatus nsb_tonemap(NsbContext* ctx, const float* accumulate_buffer_dev, float* out_rgba_dev, int32_t width, int32_t height,
                       const NsbTonemap* params, void* stream);
 
+/* ---- occupancy update through the edit operators ------------------------------------------------ */
+/* The arguments Testbed::update_density_grid_nerf_operator (testbed_nerf.cu:3533-3639) takes from Testbed members. */
+typedef struct {
+	uint32_t n_uniform_samples;    /* n_uniform_density_grid_samples: cells drawn with threshold -0.01 (any trained cell) */
+	uint32_t n_nonuniform_samples; /* n_nonuniform_density_grid_samples: cells drawn with threshold NERF_MIN_OPTICAL_THICKNESS */
+	int32_t  reset_grid;           /* reset_grid: zero the running grid first (:3558) */
+	int32_t  n_cascades;           /* m_nerf.max_cascade + 1 */
+	float    decay;                /* m_nerf.training.density_grid_decay (0.95) */
+	uint32_t ema_step;             /* m_nerf.density_grid_ema_step BEFORE the call (the host increments it afterwards, :3636) */
+	uint64_t rng_state, rng_inc;   /* m_rng (tcnn pcg32) BEFORE the call; the reference advances it by 2^32 after each of the
+	                                  two sample-generation launches (:3576,:3589) — the host mirror does the same */
+	float    train_aabb_min[3], train_aabb_max[3]; /* m_aabb */
+	int32_t  density_activation;   /* NsbActivation */
+	int32_t  apply_operators;      /* 0: behave like update_density_grid_nerf's sampling/splat without operators */
+} NsbGridUpdate;
+/* replaces Testbed::update_density_grid_nerf_operator + update_density_grid_mean_and_bitfield: draws grid samples
+ * (generate_grid_samples_nerf_nonuniform, common_nerf.cu:179-208), maps them through the uploaded operators in reverse order
+ * (EditOperator::map_positions, :3593-3599), evaluates NerfNetwork::density, activates, adds the membrane residual densities
+ * (compute_poisson_residual_density, cage_deformation.cu:341-383), max-splats into a scratch grid (:447-463), merges into the
+ * context's running density grid (ema_grid_samples_nerf, :483-506) and rebuilds the occupancy bitfield the renderer marches.
+ * The running grid is the one nsb_upload_density_grid stored (all zeros if none was uploaded). Stream-ordered. */
+NsbStatus nsb_update_density_grid(NsbContext* ctx, const NsbGridUpdate* params, void* stream);
+/* copies the context's running density grid (HOST float[5*128^3], may be NULL) and occupancy bitfield (HOST, NSB_BITFIELD_BYTES,
+ * may be NULL) back; synchronises the device. */
+NsbStatus nsb_download_density_grid(NsbContext* ctx, float* density_grid, uint8_t* bitfield);
+
 /* ---- operator-level entry points (unit parity; same device code as nsb_render) ------- */
 /* replaces NerfNetwork::inference_mixed_precision (testbed_nerf.cu:2892,2913):
  * coords_dev: n x 7 floats {pos3 (warped), dt, dir3 (warped)} = NerfCoordinate (nerf.h:73);

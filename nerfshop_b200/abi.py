@@ -92,6 +92,15 @@ class NsbTonemap(C.Structure):
     ]
 
 
+class NsbGridUpdate(C.Structure):
+    """Arguments of Testbed::update_density_grid_nerf_operator (testbed_nerf.cu:3533-3639)."""
+    _fields_ = [
+        ("n_uniform_samples", u32), ("n_nonuniform_samples", u32), ("reset_grid", i32), ("n_cascades", i32),
+        ("decay", f32), ("ema_step", u32), ("rng_state", u64), ("rng_inc", u64),
+        ("train_aabb_min", f32 * 3), ("train_aabb_max", f32 * 3), ("density_activation", i32), ("apply_operators", i32),
+    ]
+
+
 class NsbRenderStats(C.Structure):
     _fields_ = [
         ("n_rays", u64), ("n_rays_alive", u64), ("n_hit", u64), ("n_samples", u64), ("n_old_samples", u64),
@@ -103,6 +112,7 @@ class NsbRenderStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "nsb_abi_version", "nsb_last_error", "nsb_create", "nsb_destroy",
     "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_upload_density_grid", "nsb_set_edit_ops",
+    "nsb_update_density_grid", "nsb_download_density_grid",
     "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
     "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_accumulate", "nsb_tonemap",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
@@ -139,6 +149,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_upload_model.argtypes = [vp, C.POINTER(NsbModelDesc), vp, u64]
     lib.nsb_upload_occupancy.argtypes = [vp, vp, u64]
     lib.nsb_upload_density_grid.argtypes = [vp, vp, u64, vp]
+    lib.nsb_update_density_grid.argtypes = [vp, C.POINTER(NsbGridUpdate), vp]
+    lib.nsb_download_density_grid.argtypes = [vp, vp, vp]
     lib.nsb_set_edit_ops.argtypes = [vp, C.POINTER(NsbEditOp), i32]
     lib.nsb_render.argtypes = [vp, C.POINTER(NsbFrame), vp, vp, vp]
     lib.nsb_render_host.argtypes = [vp, C.POINTER(NsbFrame), vp, vp]

@@ -419,6 +419,32 @@ __device__ __forceinline__ void encode_sh4(V3 dw, __half2* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// tcnn::default_rng_t = pcg32 (M. O'Neill's PCG-XSH-RR 64/32, public algorithm; tiny-cuda-nn pcg32.h [tcnn-ext]);
+// used by generate_grid_samples_nerf_nonuniform (common_nerf.cu:179-208).
+// ------------------------------------------------------------------------------------------------
+struct Pcg32 {
+	uint64_t state, inc;
+	__host__ __device__ __forceinline__ uint32_t next_uint() {
+		uint64_t old = state;
+		state = old * 0x5851f42d4c957f2dULL + inc;
+		uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+		uint32_t rot = (uint32_t)(old >> 59u);
+		return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31u));
+	}
+	__device__ __forceinline__ float next_float() { return sub(__uint_as_float((next_uint() >> 9) | 0x3f800000u), 1.0f); }
+	__host__ __device__ __forceinline__ void advance(uint64_t delta) {  // LCG skip-ahead in O(log delta)
+		uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+		while (delta > 0) {
+			if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+			cur_plus = (cur_mult + 1) * cur_plus;
+			cur_mult *= cur_mult;
+			delta >>= 1;
+		}
+		state = acc_mult * state + acc_plus;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
 // editing — selection_utils.h:10-47, cage_deformation.cu:197-269,431-541, affine_duplication.cu:92-118
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float scalar_tp(V3 a, V3 b, V3 c) { return dot3(a, cross3(b, c)); }

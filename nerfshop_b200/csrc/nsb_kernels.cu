@@ -491,14 +491,6 @@ __global__ void k_grid_mean_partial(const float* __restrict__ grid, uint32_t n, 
 	for (int s = 128; s > 0; s >>= 1) { if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
 	if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
-__global__ void k_grid_to_bitfield(uint32_t n_bytes, const float* __restrict__ grid, uint8_t* __restrict__ bits, float thresh) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_bytes) return;
-	uint8_t b = 0;
-#pragma unroll
-	for (int j = 0; j < 8; ++j) b |= grid[(size_t)i * 8 + j] > thresh ? (uint8_t)(1u << j) : (uint8_t)0;
-	bits[i] = b;
-}
 __device__ __forceinline__ uint32_t morton3D_invert(uint32_t x) {
 	x = x & 0x49249249u;
 	x = (x | (x >> 2)) & 0xc30c30c3u;
@@ -515,6 +507,113 @@ __global__ void k_bitfield_max_pool(uint32_t n, const uint8_t* __restrict__ prev
 	for (int j = 0; j < 8; ++j) b |= prev_level[(size_t)i * 8 + j] > 0 ? (uint8_t)(1u << j) : (uint8_t)0;
 	uint32_t x = morton3D_invert(i >> 0) + GRIDSIZE / 8, y = morton3D_invert(i >> 1) + GRIDSIZE / 8, z = morton3D_invert(i >> 2) + GRIDSIZE / 8;
 	next_level[morton3D(x, y, z)] |= b;
+}
+
+// ---- occupancy update through the edit operators (testbed_nerf.cu:3533-3639) ------------------------------------------
+// One fused pass per grid sample: draw (common_nerf.cu:179-208) -> map_positions in reverse operator order (:3593-3599)
+// -> hash encode + density MLP on tcgen05 (NerfNetwork::density) -> activate (:3522-3531) -> membrane residual density
+// (cage_deformation.cu:341-383) -> max-splat (:447-463). The reference materialises positions, indices, a bool mask and the
+// 16 x N fp16 density matrix between seven launches; here a sample lives in registers/shared memory/TMEM from draw to splat.
+struct GridUpdateArgs {
+	uint32_t n_uniform, n_total, n_cascades, step;
+	uint64_t rng_state, rng_inc;
+	float amin[3], amax[3];
+	int density_activation, apply_ops;
+};
+__global__ void __launch_bounds__(128) k_density_grid_update(const DevModel m, const DevOp* __restrict__ ops, int n_ops, const GridUpdateArgs a,
+                                                             const float* __restrict__ grid, float* __restrict__ grid_tmp) {
+	extern __shared__ __align__(128) uint8_t smem_raw[];
+	tc::TileSmem& S = *reinterpret_cast<tc::TileSmem*>(smem_raw);
+	const uint32_t tid = threadIdx.x;
+	const uint32_t tmem_base = tc::tile_setup(S, m.w_image);
+	uint32_t phase = 0;
+	const uint32_t n_padded = ((a.n_total + 127u) / 128u) * 128u;
+	for (uint32_t base = blockIdx.x * 128u; base < n_padded; base += gridDim.x * 128u) {
+		const uint32_t i = base + tid;
+		const bool valid = i < a.n_total;
+		V3 pw = v3(0, 0, 0), dw = v3(0.5f, 0.5f, 0.5f);
+		uint32_t idx = 0;
+		if (valid) {
+			// the reference runs two launches (uniform: any trained cell; non-uniform: occupied cells), m_rng advanced by 2^32 between
+			const bool second = i >= a.n_uniform;
+			uint32_t li = second ? i - a.n_uniform : i;
+			const uint32_t n_el = second ? a.n_total - a.n_uniform : a.n_uniform;
+			const float thresh = second ? 0.01f : -0.01f;
+			// Work assignment (not semantics): the reference's thread li draws cell (li*A + B) mod 128^3, a pseudo-random permutation,
+			// so a warp's 32 samples scatter over the whole volume. Every sample is independent and the splat is an order-free max, so
+			// thread t instead takes the sample whose first-choice cell is t mod 128^3: a warp covers a 4x4x2 Morton block of cells and
+			// its hash-grid gathers share sectors (53369 = 56924617^-1 mod 2^21). Exact for whole multiples of 128^3 samples (the reference's post-edit setting).
+			if (li < (n_el & ~(GRIDVOL - 1u)))
+				li = (li & ~(GRIDVOL - 1u)) | ((((li & (GRIDVOL - 1u)) - 96925573u) * 53369u - a.step * n_el) & (GRIDVOL - 1u));
+			Pcg32 rng;
+			rng.state = a.rng_state; rng.inc = a.rng_inc;
+			if (second) rng.advance(1ull << 32);
+			rng.advance((uint64_t)(li * 4u));
+			const uint32_t level = (uint32_t)mul(rng.next_float(), (float)a.n_cascades) % a.n_cascades;
+			for (uint32_t j = 0; j < 10; ++j) {
+				idx = ((li + a.step * n_el) * 56924617u + j * 19349663u + 96925573u) % GRIDVOL;
+				idx += level * GRIDVOL;
+				if (grid[idx] > thresh) break;
+			}
+			const uint32_t pos_idx = idx % GRIDVOL;
+			const float x = (float)morton3D_invert(pos_idx >> 0), y = (float)morton3D_invert(pos_idx >> 1), z = (float)morton3D_invert(pos_idx >> 2);
+			const float rx = rng.next_float(), ry = rng.next_float(), rz = rng.next_float();
+			const float sc = __uint_as_float((127u + level) << 23);  // scalbnf(1, level)
+			V3 p = v3(fma_(sub(div_(add(x, rx), (float)GRIDSIZE), 0.5f), sc, 0.5f), fma_(sub(div_(add(y, ry), (float)GRIDSIZE), 0.5f), sc, 0.5f),
+			          fma_(sub(div_(add(z, rz), (float)GRIDSIZE), 0.5f), sc, 0.5f));
+			pw = warp_position(p, a.amin, a.amax);
+			if (a.apply_ops && n_ops > 0) {
+				bool empty = false;  // the reference fills empty_mask here but its consumer clear_empty_space is a no-op (:2759-2770)
+				V3 d = dw;
+				map_one(ops, n_ops, pw, d, empty);
+			}
+		}
+		uint32_t dens[8], rgbo[8];
+		encode_to_a32(S, m, valid, pw, tid);
+		tc::run_network(S, tmem_base, phase, dw, true, dens, rgbo);
+		if (valid) {
+			__half h = __float2half_rn(network_to_density(__half2float(__ushort_as_half((unsigned short)(dens[0] & 0xffffu))), a.density_activation));
+			if (a.apply_ops) {
+				for (int o = n_ops - 1; o >= 0; --o) {  // :3612-3620; looked up at the MAPPED position, as the reference does
+					const DevOp& op = ops[o];
+					if (op.type != 0 || !op.apply_poisson || !op.has_poisson_data || op.n_tets == 0) continue;
+					V3 p = unwarp_position(pw, op.amin, op.amax);
+					if (!box_contains(op.bmin, op.bmax, p)) continue;
+					float b[4];
+					int t = find_tet(op, p, b);
+					if (t < 0) continue;
+					uint4 tv = __ldg(reinterpret_cast<const uint4*>(op.tets) + t);
+					float res = bary_mix1(b, __ldg(op.rd + tv.x), __ldg(op.rd + tv.y), __ldg(op.rd + tv.z), __ldg(op.rd + tv.w));
+					h = __hadd(h, __float2half_rn(res));
+				}
+			}
+			const float optical_thickness = mul(__half2float(h), MIN_STEP());
+			atomicMax(reinterpret_cast<unsigned int*>(grid_tmp) + idx, __float_as_uint(optical_thickness));  // uint order == float order for >= 0
+		}
+	}
+	tc::tile_teardown(S, tmem_base);
+}
+__global__ void k_ema_grid(uint32_t n, float decay, float* __restrict__ grid, const float* __restrict__ grid_tmp) {  // :483-506
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float prev = grid[i];
+	grid[i] = prev < 0.0f ? prev : fmaxf(mul(prev, decay), grid_tmp[i]);
+}
+__global__ void k_grid_mean_final(const double* __restrict__ partial, uint32_t n_blocks, uint32_t n0, float* __restrict__ thresh_out) {
+	double sum = 0.0;
+	for (uint32_t k = 0; k < n_blocks; ++k) sum += partial[k];  // fixed order
+	const float mean = (float)(sum / (double)n0);
+	thresh_out[0] = mean < 0.01f ? mean : 0.01f;  // std::min(NERF_MIN_OPTICAL_THICKNESS(), mean) (:524)
+	thresh_out[1] = mean;
+}
+__global__ void k_grid_to_bitfield_dev(uint32_t n_bytes, const float* __restrict__ grid, uint8_t* __restrict__ bits, const float* __restrict__ thresh_ptr) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_bytes) return;
+	const float thresh = thresh_ptr[0];
+	uint8_t b = 0;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) b |= grid[(size_t)i * 8 + j] > thresh ? (uint8_t)(1u << j) : (uint8_t)0;
+	bits[i] = b;
 }
 
 // ---- frame post-process: accumulate_kernel (render_buffer.cu:217-258) and tonemap_kernel (:471-499) -------------------
@@ -627,6 +726,7 @@ struct NsbContext {
 	int sm_count = 0;
 	int ctas_per_sm = 1;
 	int inference_ctas_per_sm = 1;
+	int grid_update_ctas_per_sm = 1;
 	bool has_model = false, has_occ = false;
 	NsbModelDesc desc{};
 	DevModel model{};
@@ -634,6 +734,10 @@ struct NsbContext {
 	uint8_t* d_wimage = nullptr;
 	__half* d_wrow = nullptr;
 	uint8_t* d_bitfield = nullptr;
+	float* d_density_grid = nullptr;   // running density grid, 5 x 128^3 (Testbed::Nerf::density_grid, testbed.h:622)
+	float* d_density_tmp = nullptr;    // density_grid_tmp scratch of an update
+	double* d_mean_partial = nullptr;
+	float* d_thresh = nullptr;         // [0] bitfield threshold, [1] mean of cascade 0
 	DevOp* d_ops = nullptr;
 	int n_ops = 0;
 	int any_poisson = 0;
@@ -718,6 +822,8 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RenderSmem)));
 	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
 	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
+	CU(cudaFuncSetAttribute(k_density_grid_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
+	CU(cudaFuncSetAttribute(k_density_grid_update, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	// Persistent grid = SMs x resident CTAs. Residency is bounded by registers (128/thread -> 4), shared memory
 	// (45 KB -> 5 of 227 KB; the carve-out is requested explicitly, the default heuristic picks a small one) and
 	// TMEM (64 of 512 columns per CTA -> 8).
@@ -742,6 +848,11 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 		c->inference_ctas_per_sm = r < by_smem_tile ? r : by_smem_tile;
 		if (c->inference_ctas_per_sm > 8) c->inference_ctas_per_sm = 8;
 		if (c->inference_ctas_per_sm < 1) c->inference_ctas_per_sm = 1;
+		CU(cudaFuncGetAttributes(&fi, k_density_grid_update));
+		r = fi.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fi.numRegs * 128)) : 4;
+		c->grid_update_ctas_per_sm = r < by_smem_tile ? r : by_smem_tile;
+		if (c->grid_update_ctas_per_sm > 8) c->grid_update_ctas_per_sm = 8;
+		if (c->grid_update_ctas_per_sm < 1) c->grid_update_ctas_per_sm = 1;
 	}
 	if (const char* e = getenv("NSB_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->ctas_per_sm = v; }
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
@@ -768,6 +879,7 @@ extern "C" NsbStatus nsb_destroy(NsbContext* c) {
 	cudaDeviceSynchronize();
 	free_ops(c);
 	cudaFree(c->d_grid); cudaFree(c->d_wimage); cudaFree(c->d_wrow); cudaFree(c->d_bitfield);
+	cudaFree(c->d_density_grid); cudaFree(c->d_density_tmp); cudaFree(c->d_mean_partial); cudaFree(c->d_thresh);
 	cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_fb); cudaFree(c->d_depth); cudaFree(c->d_list);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
@@ -836,36 +948,89 @@ extern "C" NsbStatus nsb_upload_occupancy(NsbContext* c, const uint8_t* bitfield
 	return NSB_OK;
 }
 
+static NsbStatus ensure_grid_buffers(NsbContext* c) {
+	const uint32_t n_blocks = (GRIDVOL + 256 * 64 - 1) / (256 * 64);
+	if (!c->d_density_grid) {
+		CU(cudaMalloc(&c->d_density_grid, (size_t)NSB_GRID_CELLS * 4));
+		CU(cudaMemset(c->d_density_grid, 0, (size_t)NSB_GRID_CELLS * 4));
+	}
+	if (!c->d_mean_partial) CU(cudaMalloc(&c->d_mean_partial, n_blocks * sizeof(double)));
+	if (!c->d_thresh) CU(cudaMalloc(&c->d_thresh, 2 * sizeof(float)));
+	if (!c->d_bitfield) CU(cudaMalloc(&c->d_bitfield, NSB_BITFIELD_BYTES));
+	return NSB_OK;
+}
+// Testbed::update_density_grid_mean_and_bitfield (testbed_nerf.cu:3642-3658), device-resident and stream-ordered
+static NsbStatus rebuild_bitfield(NsbContext* c, cudaStream_t st) {
+	const uint32_t n0 = GRIDVOL, n_blocks = (n0 + 256 * 64 - 1) / (256 * 64);
+	k_grid_mean_partial<<<n_blocks, 256, 0, st>>>(c->d_density_grid, n0, c->d_mean_partial);  // reduce_sum(fmaxf(val,0)/n) over cascade 0 (:3650)
+	k_grid_mean_final<<<1, 1, 0, st>>>(c->d_mean_partial, n_blocks, n0, c->d_thresh);
+	k_grid_to_bitfield_dev<<<(NSB_BITFIELD_BYTES + 255) / 256, 256, 0, st>>>(NSB_BITFIELD_BYTES, c->d_density_grid, c->d_bitfield, c->d_thresh);
+	for (uint32_t level = 1; level < NSB_NERF_CASCADES; ++level) {
+		const uint32_t n = GRIDVOL / 64;
+		k_bitfield_max_pool<<<(n + 255) / 256, 256, 0, st>>>(n, c->d_bitfield + (size_t)(level - 1) * (GRIDVOL / 8), c->d_bitfield + (size_t)level * (GRIDVOL / 8));
+	}
+	CU(cudaGetLastError());
+	c->has_occ = true;
+	return NSB_OK;
+}
+
 extern "C" NsbStatus nsb_upload_density_grid(NsbContext* c, const float* grid, uint64_t n_floats, uint8_t* bitfield_out) {
 	if (!c || !grid) return fail(NSB_ERR_INVALID, "null argument");
 	if (n_floats != (uint64_t)NSB_GRID_CELLS) return fail(NSB_ERR_INVALID, "density grid must be 5 x 128^3 floats");
 	CU(cudaSetDevice(c->device));
 	CU(cudaDeviceSynchronize());
-	float* d_grid = nullptr;
-	double* d_partial = nullptr;
-	CU(cudaMalloc(&d_grid, n_floats * 4));
-	CU(cudaMemcpy(d_grid, grid, n_floats * 4, cudaMemcpyHostToDevice));
-	const uint32_t n0 = GRIDVOL, n_blocks = (n0 + 256 * 64 - 1) / (256 * 64);
-	CU(cudaMalloc(&d_partial, n_blocks * sizeof(double)));
-	k_grid_mean_partial<<<n_blocks, 256>>>(d_grid, n0, d_partial);
-	std::vector<double> partial(n_blocks);
-	CU(cudaMemcpy(partial.data(), d_partial, n_blocks * sizeof(double), cudaMemcpyDeviceToHost));
-	double sum = 0.0;
-	for (double p : partial) sum += p;
-	const float mean = (float)(sum / (double)n0);               // reduce_sum(fmaxf(val,0)/n) over cascade 0 (:3650)
-	const float thresh = mean < 0.01f ? mean : 0.01f;            // std::min(NERF_MIN_OPTICAL_THICKNESS(), mean) (:524)
-	if (!c->d_bitfield) CU(cudaMalloc(&c->d_bitfield, NSB_BITFIELD_BYTES));
-	k_grid_to_bitfield<<<(NSB_BITFIELD_BYTES + 255) / 256, 256>>>(NSB_BITFIELD_BYTES, d_grid, c->d_bitfield, thresh);
-	for (uint32_t level = 1; level < NSB_NERF_CASCADES; ++level) {
-		const uint32_t n = GRIDVOL / 64;
-		k_bitfield_max_pool<<<(n + 255) / 256, 256>>>(n, c->d_bitfield + (size_t)(level - 1) * (GRIDVOL / 8), c->d_bitfield + (size_t)level * (GRIDVOL / 8));
-	}
-	CU(cudaGetLastError());
+	NsbStatus st = ensure_grid_buffers(c);
+	if (st != NSB_OK) return st;
+	CU(cudaMemcpy(c->d_density_grid, grid, n_floats * 4, cudaMemcpyHostToDevice));
+	st = rebuild_bitfield(c, nullptr);
+	if (st != NSB_OK) return st;
 	CU(cudaDeviceSynchronize());
 	if (bitfield_out) CU(cudaMemcpy(bitfield_out, c->d_bitfield, NSB_BITFIELD_BYTES, cudaMemcpyDeviceToHost));
-	cudaFree(d_grid);
-	cudaFree(d_partial);
-	c->has_occ = true;
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_update_density_grid(NsbContext* c, const NsbGridUpdate* u, void* stream_) {
+	if (!c || !u) return fail(NSB_ERR_INVALID, "null argument");
+	if (!c->has_model) return fail(NSB_ERR_STATE, "nsb_upload_model has not been called");
+	if (u->n_cascades < 1 || u->n_cascades > NSB_NERF_CASCADES) return fail(NSB_ERR_INVALID, "n_cascades must be in [1, 5]");
+	const uint64_t n_total64 = (uint64_t)u->n_uniform_samples + u->n_nonuniform_samples;
+	if (n_total64 > 0xffffff00ull) return fail(NSB_ERR_INVALID, "too many grid samples");
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)stream_;
+	NsbStatus rc = ensure_grid_buffers(c);
+	if (rc != NSB_OK) return rc;
+	if (!c->d_density_tmp) CU(cudaMalloc(&c->d_density_tmp, (size_t)NSB_GRID_CELLS * 4));
+	if (u->reset_grid) CU(cudaMemsetAsync(c->d_density_grid, 0, (size_t)NSB_GRID_CELLS * 4, st));        // :3558-3560
+	CU(cudaMemsetAsync(c->d_density_tmp, 0, (size_t)NSB_GRID_CELLS * 4, st));                            // :3563
+	const uint32_t n_total = (uint32_t)n_total64;
+	if (n_total > 0) {
+		GridUpdateArgs a{};
+		a.n_uniform = u->n_uniform_samples; a.n_total = n_total; a.n_cascades = (uint32_t)u->n_cascades; a.step = u->ema_step;
+		a.rng_state = u->rng_state; a.rng_inc = u->rng_inc;
+		for (int k = 0; k < 3; ++k) { a.amin[k] = u->train_aabb_min[k]; a.amax[k] = u->train_aabb_max[k]; }
+		a.density_activation = u->density_activation; a.apply_ops = u->apply_operators ? 1 : 0;
+		uint32_t grid = (n_total + 127u) / 128u;
+		uint32_t cap = (uint32_t)(c->sm_count * c->grid_update_ctas_per_sm);
+		if (grid > cap) grid = cap;
+		k_density_grid_update<<<grid, 128, sizeof(tc::TileSmem), st>>>(c->model, c->d_ops, c->n_ops, a, c->d_density_grid, c->d_density_tmp);
+	}
+	k_ema_grid<<<(NSB_GRID_CELLS + 255) / 256, 256, 0, st>>>((uint32_t)NSB_GRID_CELLS, u->decay, c->d_density_grid, c->d_density_tmp);  // :3634
+	CU(cudaGetLastError());
+	return rebuild_bitfield(c, st);                                                                      // :3639
+}
+
+extern "C" NsbStatus nsb_download_density_grid(NsbContext* c, float* grid_out, uint8_t* bitfield_out) {
+	if (!c) return fail(NSB_ERR_INVALID, "null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	if (grid_out) {
+		if (!c->d_density_grid) return fail(NSB_ERR_STATE, "no density grid: call nsb_upload_density_grid or nsb_update_density_grid first");
+		CU(cudaMemcpy(grid_out, c->d_density_grid, (size_t)NSB_GRID_CELLS * 4, cudaMemcpyDeviceToHost));
+	}
+	if (bitfield_out) {
+		if (!c->d_bitfield || !c->has_occ) return fail(NSB_ERR_STATE, "no occupancy bitfield");
+		CU(cudaMemcpy(bitfield_out, c->d_bitfield, NSB_BITFIELD_BYTES, cudaMemcpyDeviceToHost));
+	}
 	return NSB_OK;
 }
 

@@ -62,6 +62,39 @@ class NerfRenderer:
         abi.check(self.lib, self.lib.nsb_upload_density_grid(self.ctx, g.ctypes.data, g.size, out.ctypes.data), "nsb_upload_density_grid")
         return out
 
+    def update_density_grid(self, rng, ema_step: int, n_uniform: int, n_nonuniform: int = 0, reset_grid: bool = False, n_cascades: int = 3,
+                            decay: float = 0.95, train_aabb=((-1.5, -1.5, -1.5), (2.5, 2.5, 2.5)), density_activation: int = abi.NSB_ACT_EXPONENTIAL,
+                            apply_operators: bool = True, stream: int = 0) -> None:
+        """Testbed::update_density_grid_nerf_operator (testbed_nerf.cu:3533-3639): one update of the context's running density
+        grid and occupancy bitfield through the uploaded operators. `rng` (nerfshop_b200.rng.Pcg32) is advanced like m_rng."""
+        u = abi.NsbGridUpdate()
+        u.n_uniform_samples, u.n_nonuniform_samples = int(n_uniform), int(n_nonuniform)
+        u.reset_grid, u.n_cascades, u.decay, u.ema_step = int(bool(reset_grid)), int(n_cascades), float(decay), int(ema_step)
+        u.rng_state, u.rng_inc = rng.state, rng.inc
+        u.train_aabb_min[:] = train_aabb[0]
+        u.train_aabb_max[:] = train_aabb[1]
+        u.density_activation, u.apply_operators = int(density_activation), int(bool(apply_operators))
+        abi.check(self.lib, self.lib.nsb_update_density_grid(self.ctx, C.byref(u), stream), "nsb_update_density_grid")
+        rng.advance()  # :3576
+        rng.advance()  # :3589
+        return u
+
+    def update_density_grid_nerf_render(self, state: dict, n_iterations: int, reset_grid: bool, **kw) -> None:
+        """Testbed::update_density_grid_nerf_render (testbed_nerf.cu:3514-3520): full-grid uniform updates after an edit.
+        `state` carries Testbed's members {"rng": Pcg32, "ema_step": int, "max_cascade": int}."""
+        n_casc = state["max_cascade"] + 1
+        for i in range(n_iterations):
+            self.update_density_grid(state["rng"], state["ema_step"], 128 ** 3 * n_casc, 0, reset_grid and i == 0, n_cascades=n_casc, **kw)
+            state["ema_step"] += 1  # :3636
+        _torch().cuda.synchronize(self.device)
+
+    def download_density_grid(self, want_grid: bool = True, want_bitfield: bool = True):
+        grid = np.zeros(abi.NSB_GRID_CELLS, np.float32) if want_grid else None
+        bits = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8) if want_bitfield else None
+        abi.check(self.lib, self.lib.nsb_download_density_grid(self.ctx, None if grid is None else grid.ctypes.data, None if bits is None else bits.ctypes.data),
+                  "nsb_download_density_grid")
+        return grid, bits
+
     def set_edit_operators(self, ops):
         """ops: list of (NsbEditOp, keepalive) in m_edit_operators order."""
         self._ops = list(ops or [])

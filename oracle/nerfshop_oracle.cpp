@@ -1012,6 +1012,134 @@ int orc_density_grid_to_bitfield(const float* grid /*5*128^3*/, uint8_t* bits /*
 	return 0;
 }
 
+// ---- tcnn::default_rng_t = pcg32 (PCG-XSH-RR 64/32; public algorithm, tiny-cuda-nn pcg32.h [tcnn-ext]) -------------------
+// Pinned by the PCG reference known-answer vector (seed 42, stream 54) in tests/test_oracle_units.py.
+struct Pcg32 {
+	uint64_t state, inc;
+	uint32_t next_uint() {
+		uint64_t old = state;
+		state = old * 0x5851f42d4c957f2dULL + inc;
+		uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+		uint32_t rot = (uint32_t)(old >> 59u);
+		return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31u));
+	}
+	float next_float() {
+		uint32_t u = (next_uint() >> 9) | 0x3f800000u;
+		float f;
+		memcpy(&f, &u, 4);
+		return f - 1.0f;
+	}
+	void seed(uint64_t initstate, uint64_t initseq) {
+		state = 0u;
+		inc = (initseq << 1u) | 1u;
+		next_uint();
+		state += initstate;
+		next_uint();
+	}
+	void advance(uint64_t delta) {
+		uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+		while (delta > 0) {
+			if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+			cur_plus = (cur_mult + 1) * cur_plus;
+			cur_mult *= cur_mult;
+			delta >>= 1;
+		}
+		state = acc_mult * state + acc_plus;
+	}
+};
+void orc_pcg32_seed(uint64_t initstate, uint64_t initseq, uint64_t* state_inc /*2*/) {
+	Pcg32 r; r.seed(initstate, initseq);
+	state_inc[0] = r.state; state_inc[1] = r.inc;
+}
+void orc_pcg32_next(uint64_t* state_inc, uint32_t n, uint32_t* out) {
+	Pcg32 r{state_inc[0], state_inc[1]};
+	for (uint32_t i = 0; i < n; ++i) out[i] = r.next_uint();
+	state_inc[0] = r.state;
+}
+void orc_pcg32_advance(uint64_t* state_inc, uint64_t delta) {
+	Pcg32 r{state_inc[0], state_inc[1]};
+	r.advance(delta);
+	state_inc[0] = r.state;
+}
+
+// Testbed::update_density_grid_nerf_operator (testbed_nerf.cu:3533-3639) on the host; `grid` is the running density grid
+// (in/out, 5*128^3), `bits` receives update_density_grid_mean_and_bitfield's result. `samples_out` (optional, n x 4 floats)
+// receives {mapped warped position, activated+residual density} per sample for diagnostics.
+int orc_update_density_grid(const OrcScene* s, const NsbGridUpdate* u, float* grid, uint8_t* bits, float* mean_out, float* samples_out) {
+	Model m;
+	if (!model_init(m, &s->desc, s->params, s->n_params)) return 1;
+	const uint32_t n_cells = GRIDVOL * (uint32_t)CASCADES;
+	if (u->reset_grid) memset(grid, 0, (size_t)n_cells * 4);                                   // :3558-3560
+	std::vector<uint32_t> tmp(n_cells, 0u);                                                    // density_grid_tmp, as uint bits (:3563)
+	const uint32_t n_total = u->n_uniform_samples + u->n_nonuniform_samples;
+	const Box aabb = mkbox(u->train_aabb_min, u->train_aabb_max);
+	const uint32_t n_cascades = (uint32_t)u->n_cascades;
+#pragma omp parallel for schedule(dynamic, 1024)
+	for (int64_t ii = 0; ii < (int64_t)n_total; ++ii) {
+		const uint32_t i = (uint32_t)ii;
+		// generate_grid_samples_nerf_nonuniform (common_nerf.cu:179-208): two launches, m_rng.advance() (2^32) after the first
+		const bool second = i >= u->n_uniform_samples;
+		const uint32_t li = second ? i - u->n_uniform_samples : i;
+		const uint32_t n_el = second ? u->n_nonuniform_samples : u->n_uniform_samples;
+		const float thresh = second ? 0.01f : -0.01f;
+		Pcg32 rng{u->rng_state, u->rng_inc};
+		if (second) rng.advance(1ull << 32);
+		rng.advance((uint64_t)(li * 4u));
+		const uint32_t level = (uint32_t)(rng.next_float() * (float)n_cascades) % n_cascades;
+		uint32_t idx = 0;
+		for (uint32_t j = 0; j < 10; ++j) {
+			idx = ((li + u->ema_step * n_el) * 56924617u + j * 19349663u + 96925573u) % GRIDVOL;
+			idx += level * GRIDVOL;
+			if (grid[idx] > thresh) break;
+		}
+		const uint32_t pos_idx = idx % GRIDVOL;
+		const float x = (float)morton3D_invert_(pos_idx >> 0), y = (float)morton3D_invert_(pos_idx >> 1), z = (float)morton3D_invert_(pos_idx >> 2);
+		const float rx = rng.next_float(), ry = rng.next_float(), rz = rng.next_float();
+		const float sc = scalbnf(1.0f, (int)level);
+		V3 p = v3(((x + rx) / (float)GRIDSIZE - 0.5f) * sc + 0.5f, ((y + ry) / (float)GRIDSIZE - 0.5f) * sc + 0.5f, ((z + rz) / (float)GRIDSIZE - 0.5f) * sc + 0.5f);
+		V3 pw = warp_position(p, aabb);
+		if (u->apply_operators && s->n_ops > 0) {                                               // map_positions, reverse order (:3593-3599)
+			bool empty = false;
+			V3 d = v3(0.5f, 0.5f, 0.5f);
+			map_one(s->ops, s->n_ops, pw, d, empty);
+		}
+		uint16_t o[16], d16[16];
+		network_forward(m, pw, v3(0.5f, 0.5f, 0.5f), o, d16, true);                             // NerfNetwork::density (:3601-3603)
+		uint16_t h = f2h(network_to_density(h2f(d16[0]), u->density_activation));               // activate_network_density (:3522-3531)
+		if (u->apply_operators) {
+			for (int k = s->n_ops - 1; k >= 0; --k) {                                           // compute_poisson_residual_density (:3612-3620)
+				const NsbEditOp& op = s->ops[k];
+				if (op.type != NSB_OP_CAGE || !op.apply_poisson || op.n_tets == 0 || !op.boundary_residual_density) continue;
+				Box saabb = mkbox(op.scene_aabb_min, op.scene_aabb_max);
+				Box bbox = mkbox(op.bbox_min, op.bbox_max);
+				V3 q = unwarp_position(pw, saabb);                                              // the MAPPED position (cage_deformation.cu:358-359)
+				if (!box_contains(bbox, q)) continue;
+				float b[4];
+				int t = find_tet(op, q, b);
+				if (t < 0) continue;
+				const uint32_t* tv = op.tets + 4 * (size_t)t;
+				float res = fmaf(b[3], op.boundary_residual_density[tv[3]], fmaf(b[2], op.boundary_residual_density[tv[2]],
+				            fmaf(b[1], op.boundary_residual_density[tv[1]], b[0] * op.boundary_residual_density[tv[0]])));
+				h = hadd(h, f2h(res));                                                          // half += half (:379)
+			}
+		}
+		const float ot = h2f(h) * MIN_STEP();                                                   // splat_..._already_activated (:447-463)
+		uint32_t ob;
+		memcpy(&ob, &ot, 4);
+		uint32_t* cell = &tmp[idx];
+		uint32_t cur = __atomic_load_n(cell, __ATOMIC_RELAXED);
+		while (ob > cur && !__atomic_compare_exchange_n(cell, &cur, ob, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+		if (samples_out) { samples_out[4 * (size_t)i] = pw.x; samples_out[4 * (size_t)i + 1] = pw.y; samples_out[4 * (size_t)i + 2] = pw.z; samples_out[4 * (size_t)i + 3] = h2f(h); }
+	}
+	for (uint32_t i = 0; i < n_cells; ++i) {                                                   // ema_grid_samples_nerf (:483-506)
+		float imp;
+		memcpy(&imp, &tmp[i], 4);
+		float prev = grid[i];
+		grid[i] = prev < 0.0f ? prev : fmaxf(prev * u->decay, imp);
+	}
+	return orc_density_grid_to_bitfield(grid, bits, mean_out);
+}
+
 int orc_set_threads(int n) {
 #ifdef _OPENMP
 	if (n > 0) omp_set_num_threads(n);

@@ -68,6 +68,13 @@ def lib() -> C.CDLL:
         l.orc_render.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_void_p, C.POINTER(OrcStats), C.c_void_p]
         l.orc_set_threads.argtypes = [C.c_int]
         l.orc_density_grid_to_bitfield.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        l.orc_pcg32_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+        l.orc_pcg32_seed.restype = None
+        l.orc_pcg32_next.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        l.orc_pcg32_next.restype = None
+        l.orc_pcg32_advance.argtypes = [C.c_void_p, C.c_uint64]
+        l.orc_pcg32_advance.restype = None
+        l.orc_update_density_grid.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbGridUpdate), C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
         l.orc_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         l.orc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.NsbTonemap)]
         _lib = l
@@ -142,6 +149,17 @@ class Oracle:
         assert self.lib.orc_march_trace(C.byref(self.scene), C.byref(frame), _ptr(pixels), n, max_samples, _ptr(rec), _ptr(idx), _ptr(cnt)) == 0
         return rec, idx, cnt
 
+    def update_density_grid(self, params: "abi.NsbGridUpdate", grid: np.ndarray, want_samples: bool = False):
+        """Testbed::update_density_grid_nerf_operator on the host. Returns (grid, bitfield, mean[, samples])."""
+        grid = np.ascontiguousarray(grid, np.float32).reshape(-1).copy()
+        bits = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8)
+        mean = C.c_float()
+        n = params.n_uniform_samples + params.n_nonuniform_samples
+        samples = np.zeros((n, 4), np.float32) if want_samples else None
+        rc = self.lib.orc_update_density_grid(C.byref(self.scene), C.byref(params), _ptr(grid), _ptr(bits), C.byref(mean), None if samples is None else _ptr(samples))
+        assert rc == 0
+        return (grid, bits, mean.value, samples) if want_samples else (grid, bits, mean.value)
+
     def render(self, frame: abi.NsbFrame, background: np.ndarray | None = None, want_margin: bool = False):
         W, H = frame.width, frame.height
         fb = np.zeros((H, W, 4), np.float32) if background is None else np.ascontiguousarray(background, np.float32).copy()
@@ -151,6 +169,22 @@ class Oracle:
         rc = self.lib.orc_render(C.byref(self.scene), C.byref(frame), _ptr(fb), _ptr(depth), C.byref(stats), None if margin is None else _ptr(margin))
         assert rc == 0
         return fb, depth, stats, margin
+
+
+def pcg32_seed(initstate: int, initseq: int):
+    st = np.zeros(2, np.uint64)
+    lib().orc_pcg32_seed(initstate, initseq, _ptr(st))
+    return st
+
+
+def pcg32_next(st: np.ndarray, n: int) -> np.ndarray:
+    out = np.zeros(n, np.uint32)
+    lib().orc_pcg32_next(_ptr(st), n, _ptr(out))
+    return out
+
+
+def pcg32_advance(st: np.ndarray, delta: int) -> None:
+    lib().orc_pcg32_advance(_ptr(st), delta)
 
 
 def accumulate(frame: np.ndarray, acc: np.ndarray, spp: int, color_space: int = 0) -> np.ndarray:
