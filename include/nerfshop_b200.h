@@ -294,6 +294,21 @@ NsbStatus nsb_poisson_residuals(NsbContext* ctx, const float* coords_dev, uint32
 NsbStatus nsb_march_trace(NsbContext* ctx, const NsbFrame* frame, const uint32_t* pixels_dev, uint32_t n_pixels,
                           uint32_t max_samples, float* rec_dev, uint32_t* idx_dev, uint32_t* count_dev, void* stream);
 
+/* ---- per-edit rebuild on the device --------------------------------------------------------------
+ * What GrowingSelection::update_tet_mesh (growing_selection.cu:1615) does on the host per gizmo drag, for the cage operator at
+ * index op_index of the list given to nsb_set_edit_ops, without moving the operator's arrays off the device:
+ *   Cage::interpolate_with_mvc (cage.cu:39-55) -> TetMesh::post_update_vertices (tet_mesh.cu:13-20) ->
+ *   TetMesh::update_local_rotations (tet_mesh.cu:38-74) -> TetMesh::build_tet_grid (tet_mesh.cu:369-667; upload :651-667). */
+/* weights: HOST float [n_vertices x n_cage_vertices] of Cage::compute_mvc (cage.cu:7-36), computed once per cage. */
+NsbStatus nsb_cage_attach_mvc(NsbContext* ctx, int32_t op_index, const float* weights, uint32_t n_cage_vertices);
+/* cage_vertices: HOST float [n_cage_vertices x 3], the dragged cage. Rewrites the operator's vertices, boxes, rotations (if it
+ * was uploaded with local_rotations) and tet lookup table in place. Synchronises the stream once (the list length). */
+NsbStatus nsb_cage_deform(NsbContext* ctx, int32_t op_index, const float* cage_vertices, uint32_t n_cage_vertices, void* stream);
+/* Reads an operator's current arrays back (any pointer may be NULL): vertices [3*n_vertices], rotations [9*n_tets],
+ * lut_offsets [NSB_GRID_CELLS+1], lut_idx [idx_capacity >= *n_idx], boxes [12] = bbox min,max, warped bbox min,max. */
+NsbStatus nsb_cage_download(NsbContext* ctx, int32_t op_index, float* vertices, float* rotations, uint32_t* lut_offsets, uint32_t* lut_idx,
+                            uint64_t idx_capacity, uint64_t* n_idx, float* boxes);
+
 /* ---- host-side geometry (the per-edit level; reference runs these on the CPU too) -------- */
 /* replaces TetMesh::build_tet_grid (tet_mesh.cu:369-667): CSR tet lookup over 5x128^3 cells for the
  * given vertex set. offsets: [NSB_GRID_CELLS+1]; idx: caller buffer of capacity idx_capacity; *n_idx = needed.

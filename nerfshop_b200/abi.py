@@ -112,7 +112,7 @@ class NsbRenderStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "nsb_abi_version", "nsb_last_error", "nsb_create", "nsb_destroy",
     "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_upload_density_grid", "nsb_set_edit_ops",
-    "nsb_update_density_grid", "nsb_download_density_grid",
+    "nsb_update_density_grid", "nsb_download_density_grid", "nsb_cage_attach_mvc", "nsb_cage_deform", "nsb_cage_download",
     "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
     "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_accumulate", "nsb_tonemap",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
@@ -151,6 +151,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_upload_density_grid.argtypes = [vp, vp, u64, vp]
     lib.nsb_update_density_grid.argtypes = [vp, C.POINTER(NsbGridUpdate), vp]
     lib.nsb_download_density_grid.argtypes = [vp, vp, vp]
+    lib.nsb_cage_attach_mvc.argtypes = [vp, i32, vp, u32]
+    lib.nsb_cage_deform.argtypes = [vp, i32, vp, u32, vp]
+    lib.nsb_cage_download.argtypes = [vp, i32, vp, vp, vp, vp, u64, C.POINTER(u64), vp]
     lib.nsb_set_edit_ops.argtypes = [vp, C.POINTER(NsbEditOp), i32]
     lib.nsb_render.argtypes = [vp, C.POINTER(NsbFrame), vp, vp, vp]
     lib.nsb_render_host.argtypes = [vp, C.POINTER(NsbFrame), vp, vp]

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -705,6 +706,7 @@ __global__ void k_pack_tiles(const float4* __restrict__ fb, const float* __restr
 // =====================================================================================================
 // host side: context, uploads, C ABI
 // =====================================================================================================
+#include "nsb_edit_rebuild.cuh"
 static thread_local std::string g_last_error;
 static NsbStatus fail(NsbStatus s, const char* fmt, ...) {
 	char buf[512];
@@ -742,6 +744,17 @@ struct NsbContext {
 	int n_ops = 0;
 	int any_poisson = 0;
 	std::vector<void*> op_allocs;
+	std::vector<DevOp> h_ops;          // host copy of d_ops (pointers are device pointers)
+	struct CageRebuild {               // device scratch of nsb_cage_deform, one per operator slot
+		float* d_mvc = nullptr; uint32_t n_cv = 0, n_vertices = 0;
+		float* d_cage = nullptr;
+		uint32_t* d_counts = nullptr; uint32_t* d_block_sums = nullptr; uint32_t* d_total = nullptr;
+		nsb::rebuild::Mark* d_marks = nullptr; uint32_t marks_cap = 0; unsigned int* d_n_marks = nullptr;
+		uint32_t* d_idx = nullptr; uint64_t idx_cap = 0;   // owned replacement of the uploaded tet_lut_idx once it had to grow
+		float* d_boxes = nullptr;      // [12] bbox min/max, warped min/max; [12..17] scene aabb
+		uint64_t n_idx = 0;
+	};
+	std::vector<CageRebuild> rb;
 	uint32_t* d_counters = nullptr;  // [0] rays queued by k_prepare_rays, [1] fetch cursor of k_render_fused
 	unsigned long long* d_stats = nullptr;
 	RayRec* d_list = nullptr;
@@ -867,6 +880,12 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 static void free_ops(NsbContext* c) {
 	for (void* p : c->op_allocs) cudaFree(p);
 	c->op_allocs.clear();
+	for (auto& r : c->rb) {
+		cudaFree(r.d_mvc); cudaFree(r.d_cage); cudaFree(r.d_counts); cudaFree(r.d_block_sums); cudaFree(r.d_total); cudaFree(r.d_marks);
+		cudaFree(r.d_n_marks); cudaFree(r.d_idx); cudaFree(r.d_boxes);
+	}
+	c->rb.clear();
+	c->h_ops.clear();
 	if (c->d_ops) cudaFree(c->d_ops);
 	c->d_ops = nullptr;
 	c->n_ops = 0;
@@ -1108,6 +1127,136 @@ extern "C" NsbStatus nsb_set_edit_ops(NsbContext* c, const NsbEditOp* ops, int32
 	CU(cudaMemcpy(c->d_ops, dev.data(), sizeof(DevOp) * n, cudaMemcpyHostToDevice));
 	c->n_ops = n;
 	c->any_poisson = any_poisson;
+	c->h_ops = dev;
+	c->rb.assign((size_t)n, NsbContext::CageRebuild{});
+	for (int i = 0; i < n; ++i) { c->rb[i].n_vertices = ops[i].type == NSB_OP_CAGE ? ops[i].n_vertices : 0; c->rb[i].n_idx = c->rb[i].idx_cap = ops[i].type == NSB_OP_CAGE ? ops[i].n_lut_idx : 0; }
+	return NSB_OK;
+}
+
+// ---- per-edit rebuild on the device ---------------------------------------------------------------
+static NsbStatus cage_slot(NsbContext* c, int32_t op_index, const char* who) {
+	if (!c) return fail(NSB_ERR_INVALID, "%s: null context", who);
+	if (op_index < 0 || op_index >= c->n_ops) return fail(NSB_ERR_INVALID, "%s: operator index %d out of range (%d uploaded)", who, op_index, c->n_ops);
+	if (c->h_ops[op_index].type != NSB_OP_CAGE || c->h_ops[op_index].n_tets == 0) return fail(NSB_ERR_INVALID, "%s: operator %d is not a cage with a tet mesh", who, op_index);
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_cage_attach_mvc(NsbContext* c, int32_t op_index, const float* weights, uint32_t n_cage_vertices) {
+	NsbStatus st = cage_slot(c, op_index, "nsb_cage_attach_mvc");
+	if (st != NSB_OK) return st;
+	if (!weights || n_cage_vertices == 0 || n_cage_vertices > 4096) return fail(NSB_ERR_INVALID, "nsb_cage_attach_mvc: bad weights / cage size");
+	CU(cudaSetDevice(c->device));
+	auto& r = c->rb[op_index];
+	cudaFree(r.d_mvc); cudaFree(r.d_cage);
+	r.d_mvc = nullptr; r.d_cage = nullptr;
+	r.n_cv = n_cage_vertices;
+	CU(cudaMalloc(&r.d_mvc, (size_t)r.n_vertices * n_cage_vertices * sizeof(float)));
+	CU(cudaMalloc(&r.d_cage, (size_t)3 * n_cage_vertices * sizeof(float)));
+	CU(cudaMemcpy(r.d_mvc, weights, (size_t)r.n_vertices * n_cage_vertices * sizeof(float), cudaMemcpyHostToDevice));
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_cage_deform(NsbContext* c, int32_t op_index, const float* cage_vertices, uint32_t n_cage_vertices, void* stream_) {
+	using namespace nsb::rebuild;
+	NsbStatus st = cage_slot(c, op_index, "nsb_cage_deform");
+	if (st != NSB_OK) return st;
+	auto& r = c->rb[op_index];
+	if (!r.d_mvc) return fail(NSB_ERR_STATE, "nsb_cage_deform: nsb_cage_attach_mvc has not been called for operator %d", op_index);
+	if (!cage_vertices || n_cage_vertices != r.n_cv) return fail(NSB_ERR_INVALID, "nsb_cage_deform: expected %u cage vertices", r.n_cv);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t s = (cudaStream_t)stream_;
+	DevOp& d = c->h_ops[op_index];
+	const uint32_t n_cells = (uint32_t)NSB_GRID_CELLS, n_scan_blocks = (n_cells + SCAN_TILE - 1) / SCAN_TILE;
+	if (!r.d_counts) {
+		CU(cudaMalloc(&r.d_counts, (size_t)n_cells * 4));
+		CU(cudaMalloc(&r.d_block_sums, (size_t)n_scan_blocks * 4));
+		CU(cudaMalloc(&r.d_total, 4));
+		CU(cudaMalloc(&r.d_n_marks, 4));
+		CU(cudaMalloc(&r.d_boxes, 18 * sizeof(float)));
+		float aabb[6] = {d.amin[0], d.amin[1], d.amin[2], d.amax[0], d.amax[1], d.amax[2]};
+		CU(cudaMemcpy(r.d_boxes + 12, aabb, sizeof(aabb), cudaMemcpyHostToDevice));
+		r.marks_cap = 1u << 20;
+		CU(cudaMalloc(&r.d_marks, (size_t)r.marks_cap * sizeof(Mark)));
+	}
+	float* d_verts = const_cast<float*>(d.verts);
+	const bool verbose = getenv("NSB_VERBOSE") != nullptr;
+	auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+	const double t_start = now();
+	double t_marked = 0, t_launched = 0;
+	// 1. Cage::interpolate_with_mvc
+	CU(cudaMemcpyAsync(r.d_cage, cage_vertices, (size_t)3 * r.n_cv * sizeof(float), cudaMemcpyHostToDevice, s));
+	k_mvc_apply<<<(r.n_vertices + 127) / 128, 128, 3 * r.n_cv * sizeof(float), s>>>(r.d_mvc, r.n_vertices, r.n_cv, r.d_cage, d_verts);
+	// 2. TetMesh::post_update_vertices, update_local_rotations
+	k_cage_bbox<<<1, 256, 0, s>>>(d_verts, r.n_vertices, r.d_boxes + 12, r.d_boxes);
+	if (d.rots) k_local_rotations<<<(d.n_tets + 63) / 64, 64, 0, s>>>(d_verts, d.orig_verts, d.tets, d.n_tets, const_cast<float*>(d.rots));
+	// 3. TetMesh::build_tet_grid: mark, scan, scatter, order
+	unsigned int n_marks = 0;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		CU(cudaMemsetAsync(r.d_counts, 0, (size_t)n_cells * 4, s));
+		CU(cudaMemsetAsync(r.d_n_marks, 0, 4, s));
+		k_tet_mark<<<d.n_tets * CASCADES, 128, 0, s>>>(d_verts, d.tets, d.n_tets, r.d_counts, r.d_marks, r.marks_cap, r.d_n_marks);
+		CU(cudaMemcpyAsync(&n_marks, r.d_n_marks, 4, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));  // one sync per edit: the list length decides the allocation
+		t_marked = now();
+		if (n_marks <= r.marks_cap) break;
+		if (attempt == 1) return fail(NSB_ERR_CUDA, "nsb_cage_deform: mark buffer overflow after regrow");
+		cudaFree(r.d_marks);
+		r.d_marks = nullptr;
+		r.marks_cap = n_marks + n_marks / 4;
+		CU(cudaMalloc(&r.d_marks, (size_t)r.marks_cap * sizeof(Mark)));
+	}
+	uint32_t* d_off = const_cast<uint32_t*>(d.lut_off);
+	k_scan_block_sums<<<n_scan_blocks, SCAN_THREADS, 0, s>>>(r.d_counts, n_cells, r.d_block_sums);
+	k_scan_sums<<<1, SCAN_THREADS, 0, s>>>(r.d_block_sums, n_scan_blocks, r.d_total);
+	k_scan_apply<<<n_scan_blocks, SCAN_THREADS, 0, s>>>(r.d_counts, n_cells, r.d_block_sums, r.d_total, d_off);
+	uint32_t* d_idx = const_cast<uint32_t*>(d.lut_idx);
+	if ((uint64_t)n_marks > r.idx_cap || !d_idx) {  // the list outgrew the array it lives in (uploaded or ours): take a larger one
+		cudaFree(r.d_idx);
+		r.d_idx = nullptr;
+		r.idx_cap = (uint64_t)n_marks + n_marks / 4 + 1;
+		CU(cudaMalloc(&r.d_idx, r.idx_cap * 4));
+		d_idx = r.d_idx;
+		d.lut_idx = r.d_idx;
+	}
+	if (n_marks) {
+		k_tet_fill<<<(n_marks + 255) / 256, 256, 0, s>>>(r.d_marks, n_marks, d_off, r.d_counts, d_idx);
+		// the counts are all zero again and the marks are consumed: reuse them as the long-cell queue and the sort scratch
+		CU(cudaMemsetAsync(r.d_n_marks, 0, 4, s));
+		k_tet_sort<<<(n_cells + 255) / 256, 256, 0, s>>>(d_off, n_cells, d_idx, r.d_counts, r.d_n_marks);
+		k_tet_sort_long<<<c->sm_count * 4, 256, 0, s>>>(d_off, d_idx, r.d_counts, r.d_n_marks, reinterpret_cast<uint32_t*>(r.d_marks));
+	}
+	r.n_idx = n_marks;
+	// 4. the operator's boxes and (possibly) its list pointer
+	float boxes[12];
+	t_launched = now();
+	CU(cudaMemcpyAsync(boxes, r.d_boxes, sizeof(boxes), cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	if (verbose)
+		fprintf(stderr, "[nsb] cage_deform op %d: %u marks; mark phase %.3f ms, launches %.3f ms, drain %.3f ms\n", op_index, n_marks, t_marked - t_start,
+		        t_launched - t_marked, now() - t_launched);
+	cp3(d.bmin, boxes); cp3(d.bmax, boxes + 3); cp3(d.wbmin, boxes + 6); cp3(d.wbmax, boxes + 9);
+	CU(cudaMemcpyAsync(c->d_ops + op_index, &d, sizeof(DevOp), cudaMemcpyHostToDevice, s));
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_cage_download(NsbContext* c, int32_t op_index, float* vertices, float* rotations, uint32_t* lut_offsets, uint32_t* lut_idx,
+                                       uint64_t idx_capacity, uint64_t* n_idx, float* boxes) {
+	NsbStatus st = cage_slot(c, op_index, "nsb_cage_download");
+	if (st != NSB_OK) return st;
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	const DevOp& d = c->h_ops[op_index];
+	const auto& r = c->rb[op_index];
+	if (vertices) CU(cudaMemcpy(vertices, d.verts, (size_t)3 * r.n_vertices * 4, cudaMemcpyDeviceToHost));
+	if (rotations) {
+		if (!d.rots) return fail(NSB_ERR_STATE, "nsb_cage_download: operator %d has no local rotations", op_index);
+		CU(cudaMemcpy(rotations, d.rots, (size_t)9 * d.n_tets * 4, cudaMemcpyDeviceToHost));
+	}
+	if (lut_offsets) CU(cudaMemcpy(lut_offsets, d.lut_off, ((size_t)NSB_GRID_CELLS + 1) * 4, cudaMemcpyDeviceToHost));
+	if (n_idx) *n_idx = r.n_idx;
+	if (lut_idx) {
+		if (idx_capacity < r.n_idx) return fail(NSB_ERR_INVALID, "nsb_cage_download: idx buffer too small (%llu needed)", (unsigned long long)r.n_idx);
+		if (r.n_idx) CU(cudaMemcpy(lut_idx, d.lut_idx, (size_t)r.n_idx * 4, cudaMemcpyDeviceToHost));
+	}
+	if (boxes) { cp3(boxes, d.bmin); cp3(boxes + 3, d.bmax); cp3(boxes + 6, d.wbmin); cp3(boxes + 9, d.wbmax); }
 	return NSB_OK;
 }
 

@@ -95,6 +95,26 @@ class NerfRenderer:
                   "nsb_download_density_grid")
         return grid, bits
 
+    # ---- per-edit rebuild on the device (GrowingSelection::update_tet_mesh, growing_selection.cu:1615) ----
+    def cage_attach_mvc(self, op_index: int, mvc_weights: np.ndarray) -> None:
+        w = np.ascontiguousarray(mvc_weights, np.float32)
+        abi.check(self.lib, self.lib.nsb_cage_attach_mvc(self.ctx, op_index, w.ctypes.data, w.shape[1]), "nsb_cage_attach_mvc")
+
+    def cage_deform(self, op_index: int, cage_vertices: np.ndarray, stream: int = 0) -> None:
+        cv = np.ascontiguousarray(cage_vertices, np.float32).reshape(-1, 3)
+        abi.check(self.lib, self.lib.nsb_cage_deform(self.ctx, op_index, cv.ctypes.data, cv.shape[0], stream), "nsb_cage_deform")
+
+    def cage_download(self, op_index: int, n_vertices: int, n_tets: int, rotations: bool = True) -> dict:
+        n = C.c_uint64()
+        abi.check(self.lib, self.lib.nsb_cage_download(self.ctx, op_index, None, None, None, None, 0, C.byref(n), None), "nsb_cage_download")
+        out = dict(vertices=np.zeros((n_vertices, 3), np.float32), rotations=np.zeros((n_tets, 9), np.float32) if rotations else None,
+                   lut_offsets=np.zeros(abi.NSB_GRID_CELLS + 1, np.uint32), lut_idx=np.zeros(max(int(n.value), 1), np.uint32), boxes=np.zeros(12, np.float32))
+        abi.check(self.lib, self.lib.nsb_cage_download(self.ctx, op_index, out["vertices"].ctypes.data, out["rotations"].ctypes.data if rotations else None,
+                                                       out["lut_offsets"].ctypes.data, out["lut_idx"].ctypes.data, out["lut_idx"].size, C.byref(n),
+                                                       out["boxes"].ctypes.data), "nsb_cage_download")
+        out["lut_idx"] = out["lut_idx"][: int(n.value)]
+        return out
+
     def set_edit_operators(self, ops):
         """ops: list of (NsbEditOp, keepalive) in m_edit_operators order."""
         self._ops = list(ops or [])
