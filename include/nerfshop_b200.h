@@ -309,6 +309,32 @@ NsbStatus nsb_cage_deform(NsbContext* ctx, int32_t op_index, const float* cage_v
 NsbStatus nsb_cage_download(NsbContext* ctx, int32_t op_index, float* vertices, float* rotations, uint32_t* lut_offsets, uint32_t* lut_idx,
                             uint64_t idx_capacity, uint64_t* n_idx, float* boxes);
 
+/* ---- membrane (Poisson) boundary values ------------------------------------------------------------ */
+/* The members GrowingSelection::compute_poisson_boundary reads (growing_selection.cu:2220-2348). */
+typedef struct {
+	uint32_t sampling_width;     /* m_poisson_editing.sh_sampling_width (10): sampling_width^2 directions per point */
+	uint32_t hemisphere_width;   /* m_hemisphere_width (10): the divisor of the stratified (u,v) */
+	uint64_t seed;               /* the reference jitters with unseeded std::rand(); here: tcnn pcg32 seeded with this value,
+	                                two draws (u then v) per sample in (point, i, j) order */
+	float    train_aabb_min[3], train_aabb_max[3]; /* m_aabb */
+	int32_t  rgb_activation, density_activation;    /* NsbActivation */
+	int32_t  is_inside;          /* is_inside: zero the density where the context's occupancy grid is empty (filter_empty :2200-2218) */
+} NsbBoundarySampling;
+/* replaces GrowingSelection::compute_poisson_boundary: points HOST [n_points x 3] (proxy-cage vertices, world units);
+ * density_out HOST [n_points] (density of each point's first sample), shs_out HOST [n_points x 27] (SH9RGB, column-major 9 x 3:
+ * the Monte-Carlo projection 4*pi/n * sum project_sh9(dir, rgb), sh_utils.cu:30-70). Directions are generated on the host like
+ * the reference does; inference, activation and the projection run on the device. Synchronises. */
+NsbStatus nsb_poisson_boundary(NsbContext* ctx, const float* points, uint32_t n_points, const NsbBoundarySampling* params,
+                               float* density_out, float* shs_out);
+/* replaces GrowingSelection::interpolate_poisson_boundary (growing_selection.cu:2350-2398) for the cage operator op_index: blends
+ * the per-cage-vertex inside/outside densities and SHs through gamma_coordinates (HOST [n_vertices x n_cage_vertices], Cage::compute_mvc
+ * with gamma) into the operator's boundary_shs / boundary_outside_density / boundary_residual_density arrays on the device, and sets
+ * residual_amplitude / apply_poisson. boundary_*_out (HOST, may be NULL) receive the arrays ([27*n_vertices], [n_vertices] x 2). */
+NsbStatus nsb_cage_set_membrane(NsbContext* ctx, int32_t op_index, const float* gamma_coordinates, uint32_t n_cage_vertices,
+                                const float* inside_density, const float* outside_density, const float* inside_shs, const float* outside_shs,
+                                float residual_amplitude, int32_t apply_poisson,
+                                float* boundary_shs_out, float* boundary_outside_density_out, float* boundary_residual_density_out);
+
 /* ---- host-side geometry (the per-edit level; reference runs these on the CPU too) -------- */
 /* replaces TetMesh::build_tet_grid (tet_mesh.cu:369-667): CSR tet lookup over 5x128^3 cells for the
  * given vertex set. offsets: [NSB_GRID_CELLS+1]; idx: caller buffer of capacity idx_capacity; *n_idx = needed.

@@ -101,6 +101,14 @@ class NsbGridUpdate(C.Structure):
     ]
 
 
+class NsbBoundarySampling(C.Structure):
+    """Members read by GrowingSelection::compute_poisson_boundary (growing_selection.cu:2220-2348)."""
+    _fields_ = [
+        ("sampling_width", u32), ("hemisphere_width", u32), ("seed", u64),
+        ("train_aabb_min", f32 * 3), ("train_aabb_max", f32 * 3), ("rgb_activation", i32), ("density_activation", i32), ("is_inside", i32),
+    ]
+
+
 class NsbRenderStats(C.Structure):
     _fields_ = [
         ("n_rays", u64), ("n_rays_alive", u64), ("n_hit", u64), ("n_samples", u64), ("n_old_samples", u64),
@@ -113,6 +121,7 @@ EXPORTED_SYMBOLS = [
     "nsb_abi_version", "nsb_last_error", "nsb_create", "nsb_destroy",
     "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_upload_density_grid", "nsb_set_edit_ops",
     "nsb_update_density_grid", "nsb_download_density_grid", "nsb_cage_attach_mvc", "nsb_cage_deform", "nsb_cage_download",
+    "nsb_poisson_boundary", "nsb_cage_set_membrane",
     "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
     "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_accumulate", "nsb_tonemap",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
@@ -154,6 +163,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_cage_attach_mvc.argtypes = [vp, i32, vp, u32]
     lib.nsb_cage_deform.argtypes = [vp, i32, vp, u32, vp]
     lib.nsb_cage_download.argtypes = [vp, i32, vp, vp, vp, vp, u64, C.POINTER(u64), vp]
+    lib.nsb_poisson_boundary.argtypes = [vp, vp, u32, C.POINTER(NsbBoundarySampling), vp, vp]
+    lib.nsb_cage_set_membrane.argtypes = [vp, i32, vp, u32, vp, vp, vp, vp, f32, i32, vp, vp, vp]
     lib.nsb_set_edit_ops.argtypes = [vp, C.POINTER(NsbEditOp), i32]
     lib.nsb_render.argtypes = [vp, C.POINTER(NsbFrame), vp, vp, vp]
     lib.nsb_render_host.argtypes = [vp, C.POINTER(NsbFrame), vp, vp]

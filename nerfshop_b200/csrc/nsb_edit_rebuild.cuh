@@ -313,5 +313,75 @@ __global__ void __launch_bounds__(256) k_tet_sort_long(const uint32_t* __restric
 	}
 }
 
+// ---- GrowingSelection::compute_poisson_boundary, device part: activate_network_output (:2182-2198), filter_empty (:2200-2218)
+// and the SH9 Monte-Carlo fit (:2334-2344, project_sh9 sh_utils.cu:30-70). One CTA per point; thread (col, k) owns coefficient k of
+// colour col and accumulates the samples in order, like the host loop. net: fp16 [16 x n_padded] row-major from the inference kernel.
+__global__ void __launch_bounds__(32) k_boundary_fit(const __half* __restrict__ net, uint32_t n_padded, const float* __restrict__ coords, uint32_t n_sh,
+                                                     int rgb_act, int density_act, const uint8_t* __restrict__ bitfield, const float* __restrict__ aabb,
+                                                     float scale, float* __restrict__ density_out, float* __restrict__ shs_out) {
+	const uint32_t pt = blockIdx.x, tid = threadIdx.x;
+	const uint32_t s0 = pt * n_sh;
+	if (tid == 31) {
+		float dens = network_to_density(__half2float(net[(size_t)3 * n_padded + s0]), density_act);
+		if (bitfield) {  // is_inside
+			V3 p = unwarp_position(v3(coords[7 * (size_t)s0], coords[7 * (size_t)s0 + 1], coords[7 * (size_t)s0 + 2]), aabb, aabb + 3);
+			int mip = mip_from_pos(p);
+			if (!bitfield_at(cascaded_grid_idx_at(p, (uint32_t)mip), (uint32_t)mip, bitfield)) dens = 0.0f;
+		}
+		density_out[pt] = dens;
+	}
+	if (tid >= 27) return;
+	const uint32_t col = tid / 9, k = tid % 9;
+	float acc = 0.0f;
+	for (uint32_t i = 0; i < n_sh; ++i) {
+		const size_t s = (size_t)s0 + i;
+		const float rgb = network_to_rgb(__half2float(net[(size_t)col * n_padded + s]), rgb_act);
+		const V3 d = unwarp_direction(v3(coords[7 * s + 4], coords[7 * s + 5], coords[7 * s + 6]));
+		float basis;
+		switch (k) {  // float constants, products left to right as the reference writes them
+			case 0: basis = 0.282095f; break;
+			case 1: basis = mul(0.488603f, d.y); break;
+			case 2: basis = mul(0.488603f, d.z); break;
+			case 3: basis = mul(0.488603f, d.x); break;
+			case 4: basis = mul(mul(1.092548f, d.x), d.y); break;
+			case 5: basis = mul(mul(1.092548f, d.y), d.z); break;
+			case 7: basis = mul(mul(1.092548f, d.x), d.z); break;
+			case 6: basis = mul(0.315392f, sub(mul(mul(3.0f, d.z), d.z), 1.0f)); break;
+			default: basis = mul(0.546274f, sub(mul(d.x, d.x), mul(d.y, d.y))); break;
+		}
+		acc = add(acc, mul(mul(rgb, basis), 1.0f));
+	}
+	shs_out[(size_t)pt * 27 + tid] = mul(acc, scale);
+}
+
+// ---- GrowingSelection::interpolate_poisson_boundary (:2350-2398): thread (tet vertex, coefficient slot); slots 0-26 the SH entries,
+// 27 the outside density, 28 the residual density. alpha_out/alpha_in/w_inside per cage vertex come from the host (libm expf).
+__global__ void k_membrane_blend(const float* __restrict__ gamma, uint32_t n_vertices, uint32_t n_cv, const float* __restrict__ alpha_out,
+                                 const float* __restrict__ w_inside, const float* __restrict__ d_in, const float* __restrict__ d_out,
+                                 const float* __restrict__ shs_in, const float* __restrict__ shs_out_, float* __restrict__ b_shs, float* __restrict__ b_od,
+                                 float* __restrict__ b_rd) {
+	const uint32_t i = blockIdx.x * blockDim.y + threadIdx.y, slot = threadIdx.x;
+	if (i >= n_vertices || slot >= 29) return;
+	const float* g = gamma + (size_t)i * n_cv;
+	if (slot < 27) {
+		float acc = 0.0f, wsum = 0.0f;
+		for (uint32_t j = 0; j < n_cv; ++j) {
+			const float sh_diff = sub(mul(1.0f, shs_out_[27 * (size_t)j + slot]), mul(w_inside[j], shs_in[27 * (size_t)j + slot]));
+			const float ga = mul(g[j], alpha_out[j]);
+			wsum = add(wsum, ga);
+			acc = add(acc, mul(ga, sh_diff));
+		}
+		b_shs[27 * (size_t)i + slot] = div_(acc, (float)((double)wsum + 1e-6));
+	} else if (slot == 27) {
+		float acc = 0.0f;
+		for (uint32_t j = 0; j < n_cv; ++j) acc = add(acc, mul(g[j], d_out[j]));
+		b_od[i] = acc;
+	} else {
+		float acc = 0.0f;
+		for (uint32_t j = 0; j < n_cv; ++j) acc = add(acc, mul(g[j], sub(d_out[j], d_in[j])));
+		b_rd[i] = fmaxf(acc, 0.0f);
+	}
+}
+
 }  // namespace rebuild
 }  // namespace nsb

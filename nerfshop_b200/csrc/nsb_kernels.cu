@@ -1237,6 +1237,121 @@ extern "C" NsbStatus nsb_cage_deform(NsbContext* c, int32_t op_index, const floa
 	CU(cudaGetLastError());
 	return NSB_OK;
 }
+// ---- membrane boundary values ---------------------------------------------------------------------
+// Host part of GrowingSelection::compute_poisson_boundary (growing_selection.cu:2235-2260): stratified directions on the sphere,
+// jittered by a seeded pcg32 instead of the reference's unseeded std::rand(). libm calls as the reference makes them.
+static void boundary_coords(const float* points, uint32_t n_points, const NsbBoundarySampling* p, std::vector<float>& coords) {
+	const uint32_t w = p->sampling_width, n_sh = w * w;
+	coords.assign((size_t)n_points * n_sh * 7, 0.0f);
+	Pcg32 rng;
+	rng.state = 0u; rng.inc = (0xda3e39cb94b95bdbULL << 1u) | 1u;  // pcg32(seed): tcnn default stream
+	rng.next_uint(); rng.state += p->seed; rng.next_uint();
+	auto next_float = [&rng] { uint32_t u = (rng.next_uint() >> 9) | 0x3f800000u; float f; memcpy(&f, &u, 4); return f - 1.0f; };
+	for (uint32_t k = 0; k < n_points; ++k)
+		for (uint32_t i = 0; i < w; ++i)
+			for (uint32_t j = 0; j < w; ++j) {
+				const float u = ((float)i + next_float()) / (float)p->hemisphere_width;
+				const float v = ((float)j + next_float()) / (float)p->hemisphere_width;
+				const float theta = (float)(2.f * M_PI * v);
+				const float phi = acosf(2.f * u - 1.f);
+				const float x = cosf(theta) * sinf(phi), y = sinf(theta) * sinf(phi), z = cosf(phi);
+				float* c = coords.data() + ((size_t)n_sh * k + (size_t)i * w + j) * 7;
+				for (int a = 0; a < 3; ++a) c[a] = (points[3 * k + a] - p->train_aabb_min[a]) / (p->train_aabb_max[a] - p->train_aabb_min[a]);  // warp_position
+				c[4] = (x + 1.0f) * 0.5f; c[5] = (y + 1.0f) * 0.5f; c[6] = (z + 1.0f) * 0.5f;                                                   // warp_direction
+			}
+}
+extern "C" NsbStatus nsb_poisson_boundary(NsbContext* c, const float* points, uint32_t n_points, const NsbBoundarySampling* p, float* density_out, float* shs_out) {
+	if (!c || !points || !p || !density_out || !shs_out) return fail(NSB_ERR_INVALID, "nsb_poisson_boundary: null argument");
+	if (!c->has_model) return fail(NSB_ERR_STATE, "nsb_upload_model has not been called");
+	if (p->sampling_width == 0 || p->sampling_width > 64 || p->hemisphere_width == 0) return fail(NSB_ERR_INVALID, "nsb_poisson_boundary: bad sampling widths");
+	if (p->is_inside && !c->has_occ) return fail(NSB_ERR_STATE, "nsb_poisson_boundary: is_inside needs an occupancy grid");
+	if (n_points == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	const uint32_t n_sh = p->sampling_width * p->sampling_width;
+	const uint64_t n64 = (uint64_t)n_points * n_sh;
+	if (n64 > 0x7fffff00ull) return fail(NSB_ERR_INVALID, "nsb_poisson_boundary: too many samples");
+	const uint32_t n = (uint32_t)n64, n_padded = next_multiple_u32(n, 128u);  // tcnn::batch_size_granularity (:2231)
+	std::vector<float> coords;
+	boundary_coords(points, n_points, p, coords);
+	float *d_coords = nullptr, *d_aabb = nullptr, *d_dens = nullptr, *d_shs = nullptr;
+	__half* d_net = nullptr;
+	auto cleanup = [&] { cudaFree(d_coords); cudaFree(d_aabb); cudaFree(d_dens); cudaFree(d_shs); cudaFree(d_net); };
+#define CUB_(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(NSB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); } } while (0)
+	CUB_(cudaMalloc(&d_coords, (size_t)n * 7 * 4));
+	CUB_(cudaMalloc(&d_aabb, 6 * 4));
+	CUB_(cudaMalloc(&d_dens, (size_t)n_points * 4));
+	CUB_(cudaMalloc(&d_shs, (size_t)n_points * 27 * 4));
+	CUB_(cudaMalloc(&d_net, (size_t)16 * n_padded * 2));
+	CUB_(cudaMemcpy(d_coords, coords.data(), (size_t)n * 7 * 4, cudaMemcpyHostToDevice));
+	float aabb[6] = {p->train_aabb_min[0], p->train_aabb_min[1], p->train_aabb_min[2], p->train_aabb_max[0], p->train_aabb_max[1], p->train_aabb_max[2]};
+	CUB_(cudaMemcpy(d_aabb, aabb, sizeof(aabb), cudaMemcpyHostToDevice));
+	uint32_t grid = n_padded / 128, cap = (uint32_t)(c->sm_count * c->inference_ctas_per_sm);
+	if (grid > cap) grid = cap;
+	k_inference<false><<<grid, 128, sizeof(tc::TileSmem)>>>(c->model, d_coords, n, d_net, n_padded);  // inference_mixed_precision (:2286)
+	const float scale = (float)(4 * M_PI / (double)n_sh);                                                // :2341
+	nsb::rebuild::k_boundary_fit<<<n_points, 32>>>(d_net, n_padded, d_coords, n_sh, p->rgb_activation, p->density_activation,
+	                                               p->is_inside ? c->d_bitfield : nullptr, d_aabb, scale, d_dens, d_shs);
+	CUB_(cudaGetLastError());
+	CUB_(cudaMemcpy(density_out, d_dens, (size_t)n_points * 4, cudaMemcpyDeviceToHost));
+	CUB_(cudaMemcpy(shs_out, d_shs, (size_t)n_points * 27 * 4, cudaMemcpyDeviceToHost));
+#undef CUB_
+	cleanup();
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_cage_set_membrane(NsbContext* c, int32_t op_index, const float* gamma, uint32_t n_cv, const float* inside_density,
+                                           const float* outside_density, const float* inside_shs, const float* outside_shs, float residual_amplitude,
+                                           int32_t apply_poisson, float* b_shs_out, float* b_od_out, float* b_rd_out) {
+	NsbStatus st = cage_slot(c, op_index, "nsb_cage_set_membrane");
+	if (st != NSB_OK) return st;
+	if (!gamma || !inside_density || !outside_density || !inside_shs || !outside_shs || n_cv == 0) return fail(NSB_ERR_INVALID, "nsb_cage_set_membrane: null argument");
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	DevOp& d = c->h_ops[op_index];
+	const uint32_t nv = c->rb[op_index].n_vertices;
+	// per-cage-vertex weights on the host, with libm like the reference (:2374-2381)
+	std::vector<float> alpha_out(n_cv), w_in(n_cv);
+	const float min_step = 1.73205080757f / 1024.0f;  // MIN_CONE_STEPSIZE
+	for (uint32_t j = 0; j < n_cv; ++j) {
+		const float a_out = 1 - expf(-outside_density[j] * min_step), a_in = 1 - expf(-inside_density[j] * min_step);
+		const float q = a_in / a_out;
+		alpha_out[j] = a_out;
+		w_in[j] = (1.f < q) ? 1.f : q;  // std::min(alpha_in / alpha_out, 1.f)
+	}
+	float *d_gamma = nullptr, *d_small = nullptr;
+	const size_t small = (size_t)n_cv * (4 + 54);
+	std::vector<float> pack(small);
+	memcpy(pack.data(), alpha_out.data(), n_cv * 4);
+	memcpy(pack.data() + n_cv, w_in.data(), n_cv * 4);
+	memcpy(pack.data() + 2 * (size_t)n_cv, inside_density, n_cv * 4);
+	memcpy(pack.data() + 3 * (size_t)n_cv, outside_density, n_cv * 4);
+	memcpy(pack.data() + 4 * (size_t)n_cv, inside_shs, (size_t)n_cv * 27 * 4);
+	memcpy(pack.data() + 31 * (size_t)n_cv, outside_shs, (size_t)n_cv * 27 * 4);
+	CU(cudaMalloc(&d_gamma, (size_t)nv * n_cv * 4));
+	c->op_allocs.push_back(d_gamma);  // released with the operator list
+	CU(cudaMalloc(&d_small, small * 4));
+	c->op_allocs.push_back(d_small);
+	CU(cudaMemcpy(d_gamma, gamma, (size_t)nv * n_cv * 4, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d_small, pack.data(), small * 4, cudaMemcpyHostToDevice));
+	if (!d.shs) { void* q; CU(cudaMalloc(&q, (size_t)nv * 27 * 4)); c->op_allocs.push_back(q); d.shs = (const float*)q; }
+	if (!d.od) { void* q; CU(cudaMalloc(&q, (size_t)nv * 4)); c->op_allocs.push_back(q); d.od = (const float*)q; }
+	if (!d.rd) { void* q; CU(cudaMalloc(&q, (size_t)nv * 4)); c->op_allocs.push_back(q); d.rd = (const float*)q; }
+	dim3 block(32, 4);
+	nsb::rebuild::k_membrane_blend<<<(nv + 3) / 4, block>>>(d_gamma, nv, n_cv, d_small, d_small + n_cv, d_small + 2 * (size_t)n_cv, d_small + 3 * (size_t)n_cv,
+	                                                        d_small + 4 * (size_t)n_cv, d_small + 31 * (size_t)n_cv, const_cast<float*>(d.shs),
+	                                                        const_cast<float*>(d.od), const_cast<float*>(d.rd));
+	CU(cudaGetLastError());
+	d.has_poisson_data = 1;
+	d.apply_poisson = apply_poisson ? 1 : 0;
+	d.amp = residual_amplitude;
+	CU(cudaMemcpy(c->d_ops + op_index, &d, sizeof(DevOp), cudaMemcpyHostToDevice));
+	int any = 0;
+	for (const DevOp& o : c->h_ops) if (o.type == NSB_OP_CAGE && o.apply_poisson && o.has_poisson_data && o.n_tets) any = 1;
+	c->any_poisson = any;
+	if (b_shs_out) CU(cudaMemcpy(b_shs_out, d.shs, (size_t)nv * 27 * 4, cudaMemcpyDeviceToHost));
+	if (b_od_out) CU(cudaMemcpy(b_od_out, d.od, (size_t)nv * 4, cudaMemcpyDeviceToHost));
+	if (b_rd_out) CU(cudaMemcpy(b_rd_out, d.rd, (size_t)nv * 4, cudaMemcpyDeviceToHost));
+	return NSB_OK;
+}
 extern "C" NsbStatus nsb_cage_download(NsbContext* c, int32_t op_index, float* vertices, float* rotations, uint32_t* lut_offsets, uint32_t* lut_idx,
                                        uint64_t idx_capacity, uint64_t* n_idx, float* boxes) {
 	NsbStatus st = cage_slot(c, op_index, "nsb_cage_download");

@@ -115,6 +115,30 @@ class NerfRenderer:
         out["lut_idx"] = out["lut_idx"][: int(n.value)]
         return out
 
+    # ---- membrane boundary values (GrowingSelection::compute_poisson_boundary / interpolate_poisson_boundary) ----
+    def poisson_boundary(self, points: np.ndarray, is_inside: bool, seed: int = 0, sampling_width: int = 10, hemisphere_width: int = 10,
+                         train_aabb=((-1.5, -1.5, -1.5), (2.5, 2.5, 2.5)), rgb_activation: int = abi.NSB_ACT_LOGISTIC,
+                         density_activation: int = abi.NSB_ACT_EXPONENTIAL):
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        p = abi.NsbBoundarySampling()
+        p.sampling_width, p.hemisphere_width, p.seed = sampling_width, hemisphere_width, seed
+        p.train_aabb_min[:] = train_aabb[0]
+        p.train_aabb_max[:] = train_aabb[1]
+        p.rgb_activation, p.density_activation, p.is_inside = rgb_activation, density_activation, int(is_inside)
+        dens, shs = np.zeros(pts.shape[0], np.float32), np.zeros((pts.shape[0], 27), np.float32)
+        abi.check(self.lib, self.lib.nsb_poisson_boundary(self.ctx, pts.ctypes.data, pts.shape[0], C.byref(p), dens.ctypes.data, shs.ctypes.data), "nsb_poisson_boundary")
+        return dens, shs, p
+
+    def cage_set_membrane(self, op_index: int, gamma: np.ndarray, inside_density, outside_density, inside_shs, outside_shs, amplitude: float = 1.0,
+                          apply: bool = True):
+        g = np.ascontiguousarray(gamma, np.float32)
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (inside_density, outside_density, inside_shs, outside_shs)]
+        nv = g.shape[0]
+        b_shs, b_od, b_rd = np.zeros((nv, 27), np.float32), np.zeros(nv, np.float32), np.zeros(nv, np.float32)
+        abi.check(self.lib, self.lib.nsb_cage_set_membrane(self.ctx, op_index, g.ctypes.data, g.shape[1], *[a.ctypes.data for a in arrs], float(amplitude), int(apply),
+                                                           b_shs.ctypes.data, b_od.ctypes.data, b_rd.ctypes.data), "nsb_cage_set_membrane")
+        return b_shs, b_od, b_rd
+
     def set_edit_operators(self, ops):
         """ops: list of (NsbEditOp, keepalive) in m_edit_operators order."""
         self._ops = list(ops or [])

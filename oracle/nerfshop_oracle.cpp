@@ -1140,6 +1140,101 @@ int orc_update_density_grid(const OrcScene* s, const NsbGridUpdate* u, float* gr
 	return orc_density_grid_to_bitfield(grid, bits, mean_out);
 }
 
+// ---- GrowingSelection::compute_poisson_boundary (growing_selection.cu:2220-2348) on the host --------------------------------
+// std::rand() jitter replaced by pcg32(seed) (two draws per sample, u then v), as include/nerfshop_b200.h documents.
+int orc_poisson_boundary(const OrcScene* s, const float* points, uint32_t n_points, const NsbBoundarySampling* p, float* density_out, float* shs_out,
+                         float* coords_out /*optional n*w*w*7*/) {
+	Model m;
+	if (!model_init(m, &s->desc, s->params, s->n_params)) return 1;
+	const uint32_t w = p->sampling_width, n_sh = w * w;
+	const Box aabb = mkbox(p->train_aabb_min, p->train_aabb_max);
+	Pcg32 rng;
+	rng.seed(p->seed, 0xda3e39cb94b95bdbULL);
+	std::vector<float> coords((size_t)n_points * n_sh * 7, 0.0f);
+	for (uint32_t k = 0; k < n_points; ++k)                                                  // :2238-2260
+		for (uint32_t i = 0; i < w; ++i)
+			for (uint32_t j = 0; j < w; ++j) {
+				float u = ((float)i + rng.next_float()) / (float)p->hemisphere_width;
+				float v = ((float)j + rng.next_float()) / (float)p->hemisphere_width;
+				float theta = (float)(2.f * M_PI * v);
+				float phi = acosf(2.f * u - 1.f);
+				float x = cosf(theta) * sinf(phi), y = sinf(theta) * sinf(phi), z = cosf(phi);
+				float* c = &coords[((size_t)n_sh * k + (size_t)i * w + j) * 7];
+				V3 pw = warp_position(v3(points[3 * k], points[3 * k + 1], points[3 * k + 2]), aabb);
+				V3 dw = warp_direction(v3(x, y, z));
+				c[0] = pw.x; c[1] = pw.y; c[2] = pw.z; c[4] = dw.x; c[5] = dw.y; c[6] = dw.z;
+			}
+	if (coords_out) memcpy(coords_out, coords.data(), coords.size() * 4);
+	const float scale = (float)(4 * M_PI / (double)n_sh);
+#pragma omp parallel for schedule(static)
+	for (int64_t k = 0; k < (int64_t)n_points; ++k) {
+		float sh[27];
+		for (int q = 0; q < 27; ++q) sh[q] = 0.0f;
+		for (uint32_t i = 0; i < n_sh; ++i) {
+			const float* c = &coords[((size_t)n_sh * k + i) * 7];
+			uint16_t o[16], d16[16];
+			network_forward(m, v3(c[0], c[1], c[2]), v3(c[4], c[5], c[6]), o, d16, false);    // inference_mixed_precision (:2286)
+			float rgb[3] = {network_to_rgb(h2f(o[0]), p->rgb_activation), network_to_rgb(h2f(o[1]), p->rgb_activation), network_to_rgb(h2f(o[2]), p->rgb_activation)};
+			if (i == 0) {                                                                     // :2325-2327, filter_empty :2200-2218
+				float dens = network_to_density(h2f(o[3]), p->density_activation);
+				if (p->is_inside) {
+					V3 pos = unwarp_position(v3(c[0], c[1], c[2]), aabb);
+					int mip = mip_from_pos(pos);
+					if (!s->bitfield || !bitfield_at(cascaded_grid_idx_at(pos, (uint32_t)mip), (uint32_t)mip, s->bitfield)) dens = 0.0f;
+				}
+				density_out[k] = dens;
+			}
+			V3 d = unwarp_direction(v3(c[4], c[5], c[6]));
+			for (int col = 0; col < 3; ++col) {                                               // project_sh9 (sh_utils.cu:30-70), domega = 1
+				float* q = sh + 9 * col;
+				const float r = rgb[col];
+				float cc = 0.282095f;
+				q[0] += r * cc * 1.0f;
+				cc = 0.488603f;
+				q[1] += r * (cc * d.y) * 1.0f;
+				q[2] += r * (cc * d.z) * 1.0f;
+				q[3] += r * (cc * d.x) * 1.0f;
+				cc = 1.092548f;
+				q[4] += r * (cc * d.x * d.y) * 1.0f;
+				q[5] += r * (cc * d.y * d.z) * 1.0f;
+				q[7] += r * (cc * d.x * d.z) * 1.0f;
+				cc = 0.315392f;
+				q[6] += r * (cc * (3 * d.z * d.z - 1)) * 1.0f;
+				cc = 0.546274f;
+				q[8] += r * (cc * (d.x * d.x - d.y * d.y)) * 1.0f;
+			}
+		}
+		for (int q = 0; q < 27; ++q) shs_out[(size_t)k * 27 + q] = sh[q] * scale;                // :2341
+	}
+	return 0;
+}
+// ---- GrowingSelection::interpolate_poisson_boundary (growing_selection.cu:2350-2398) --------------------------------------
+int orc_membrane_blend(const float* gamma, uint32_t n_vertices, uint32_t n_cv, const float* inside_density, const float* outside_density,
+                       const float* inside_shs, const float* outside_shs, float* b_shs, float* b_od, float* b_rd) {
+	for (uint32_t i = 0; i < n_vertices; ++i) {
+		float sum = 0.0f, od = 0.0f, rd = 0.0f, sh[27];
+		for (int q = 0; q < 27; ++q) sh[q] = 0.0f;
+		for (uint32_t j = 0; j < n_cv; ++j) {
+			float alpha_out = 1 - expf(-outside_density[j] * MIN_STEP());
+			float alpha_in = 1 - expf(-inside_density[j] * MIN_STEP());
+			float w_outside = 1.f;
+			float w_inside = std::min(alpha_in / alpha_out, 1.f);
+			float g = gamma[(size_t)i * n_cv + j];
+			sum += g * alpha_out;
+			for (int q = 0; q < 27; ++q) {
+				float sh_diff = w_outside * outside_shs[27 * (size_t)j + q] - w_inside * inside_shs[27 * (size_t)j + q];
+				sh[q] += g * alpha_out * sh_diff;
+			}
+			od += g * outside_density[j];
+			rd += g * (outside_density[j] - inside_density[j]);
+		}
+		for (int q = 0; q < 27; ++q) b_shs[27 * (size_t)i + q] = sh[q] / (float)(sum + 1e-6);
+		b_od[i] = od;
+		b_rd[i] = std::max(rd, 0.f);
+	}
+	return 0;
+}
+
 int orc_set_threads(int n) {
 #ifdef _OPENMP
 	if (n > 0) omp_set_num_threads(n);

@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         l.orc_pcg32_advance.argtypes = [C.c_void_p, C.c_uint64]
         l.orc_pcg32_advance.restype = None
         l.orc_update_density_grid.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbGridUpdate), C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
+        l.orc_poisson_boundary.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.POINTER(abi.NsbBoundarySampling), C.c_void_p, C.c_void_p, C.c_void_p]
+        l.orc_membrane_blend.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 7
         l.orc_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         l.orc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.NsbTonemap)]
         _lib = l
@@ -160,6 +162,15 @@ class Oracle:
         assert rc == 0
         return (grid, bits, mean.value, samples) if want_samples else (grid, bits, mean.value)
 
+    def poisson_boundary(self, points: np.ndarray, params: "abi.NsbBoundarySampling", want_coords: bool = False):
+        """GrowingSelection::compute_poisson_boundary: (density [n], shs [n, 27][, coords])."""
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        n = pts.shape[0]
+        dens, shs = np.zeros(n, np.float32), np.zeros((n, 27), np.float32)
+        coords = np.zeros((n * params.sampling_width ** 2, 7), np.float32) if want_coords else None
+        assert self.lib.orc_poisson_boundary(C.byref(self.scene), _ptr(pts), n, C.byref(params), _ptr(dens), _ptr(shs), None if coords is None else _ptr(coords)) == 0
+        return (dens, shs, coords) if want_coords else (dens, shs)
+
     def render(self, frame: abi.NsbFrame, background: np.ndarray | None = None, want_margin: bool = False):
         W, H = frame.width, frame.height
         fb = np.zeros((H, W, 4), np.float32) if background is None else np.ascontiguousarray(background, np.float32).copy()
@@ -185,6 +196,16 @@ def pcg32_next(st: np.ndarray, n: int) -> np.ndarray:
 
 def pcg32_advance(st: np.ndarray, delta: int) -> None:
     lib().orc_pcg32_advance(_ptr(st), delta)
+
+
+def membrane_blend(gamma, inside_density, outside_density, inside_shs, outside_shs):
+    """GrowingSelection::interpolate_poisson_boundary: (boundary_shs [nv, 27], outside_density [nv], residual_density [nv])."""
+    g = np.ascontiguousarray(gamma, np.float32)
+    nv, ncv = g.shape
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (inside_density, outside_density, inside_shs, outside_shs)]
+    b_shs, b_od, b_rd = np.zeros((nv, 27), np.float32), np.zeros(nv, np.float32), np.zeros(nv, np.float32)
+    assert lib().orc_membrane_blend(_ptr(g), nv, ncv, *[_ptr(a) for a in arrs], _ptr(b_shs), _ptr(b_od), _ptr(b_rd)) == 0
+    return b_shs, b_od, b_rd
 
 
 def accumulate(frame: np.ndarray, acc: np.ndarray, spp: int, color_space: int = 0) -> np.ndarray:
