@@ -93,6 +93,30 @@ class CageDeformation:
         self._grid(self.original_vertices, off, self.original_bitfield)  # build_original_tet_grid: canonical occupancy
         self.update_tet_mesh()
 
+    @classmethod
+    def from_arrays(cls, scene_aabb_min, scene_aabb_max, cage_original, cage_vertices, cage_triangles, tet_original_vertices, tets, mvc,
+                    gamma_coordinates=None, copy=False, local_rotations=True):
+        """An operator restored from saved arrays (GrowingSelection(json) + TetMesh(json), growing_selection.cu:81-117): the MVC
+        weights are taken as stored, the deformed vertices / rotations / lookup table are rebuilt (build_tet_grid, :114)."""
+        self = cls.__new__(cls)
+        self.lib = abi.load_library()
+        self.aabb_min, self.aabb_max = np.asarray(scene_aabb_min, np.float32), np.asarray(scene_aabb_max, np.float32)
+        self.cage_original = np.ascontiguousarray(cage_original, np.float32).reshape(-1, 3)
+        self.cage_vertices = np.ascontiguousarray(cage_vertices, np.float32).reshape(-1, 3)
+        self.cage_triangles = np.ascontiguousarray(cage_triangles, np.uint32).reshape(-1, 3)
+        self.original_vertices = np.ascontiguousarray(tet_original_vertices, np.float32).reshape(-1, 3)
+        self.vertices = self.original_vertices.copy()
+        self.tets = np.ascontiguousarray(tets, np.uint32).reshape(-1, 4)
+        self.copy, self.use_local_rotations = bool(copy), bool(local_rotations)
+        self.apply_poisson, self.residual_amplitude = False, 1.0
+        self.boundary_shs = self.boundary_outside_density = self.boundary_residual_density = None
+        self.mvc = np.ascontiguousarray(mvc, np.float32).reshape(self.original_vertices.shape[0], self.cage_original.shape[0])
+        self.gamma_coordinates = self.mvc if gamma_coordinates is None else np.ascontiguousarray(gamma_coordinates, np.float32).reshape(self.mvc.shape)
+        self.original_bitfield = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8)
+        self._grid(self.original_vertices, np.zeros(abi.NSB_GRID_CELLS + 1, np.uint32), self.original_bitfield)
+        self.update_tet_mesh()
+        return self
+
     def _grid(self, verts, offsets, bitfield):
         n = C.c_uint64()
         st = self.lib.nsb_build_tet_grid(verts.ctypes.data, verts.shape[0], self.tets.ctypes.data, self.tets.shape[0], offsets.ctypes.data, None, 0,
