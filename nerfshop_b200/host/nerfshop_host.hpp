@@ -90,6 +90,16 @@ public:
 		m_rendered = true;
 		return 0;  // asynchronous: n_hit is available from stats() (the reference synchronises here, :2998-3000)
 	}
+	// ---- per-edit work kept on the device ----
+	// GrowingSelection::update_tet_mesh for operator i after a gizmo drag (growing_selection.cu:1615): no re-upload.
+	void attach_mvc(size_t i, const float* mvc_weights, uint32_t n_cage_vertices) { check(nsb_cage_attach_mvc(m_ctx->get(), (int32_t)i, mvc_weights, n_cage_vertices), "nsb_cage_attach_mvc"); }
+	void deform_cage(size_t i, const float* cage_vertices, uint32_t n_cage_vertices, void* stream) { check(nsb_cage_deform(m_ctx->get(), (int32_t)i, cage_vertices, n_cage_vertices, stream), "nsb_cage_deform"); }
+	// GrowingSelection::interpolate_poisson_boundary (growing_selection.cu:2350-2398)
+	void set_membrane(size_t i, const float* gamma, uint32_t n_cage_vertices, const float* d_in, const float* d_out, const float* shs_in, const float* shs_out, float amplitude, bool apply) {
+		check(nsb_cage_set_membrane(m_ctx->get(), (int32_t)i, gamma, n_cage_vertices, d_in, d_out, shs_in, shs_out, amplitude, apply ? 1 : 0, nullptr, nullptr, nullptr), "nsb_cage_set_membrane");
+	}
+	// Testbed::update_density_grid_nerf_render (testbed_nerf.cu:3514-3520): the caller owns m_rng / density_grid_ema_step like Testbed does.
+	void update_density_grid(const NsbGridUpdate& u, void* stream) { check(nsb_update_density_grid(m_ctx->get(), &u, stream), "nsb_update_density_grid"); }
 	NsbRenderStats stats() const { NsbRenderStats s{}; check(nsb_get_stats(m_ctx->get(), &s), "nsb_get_stats"); return s; }
 	void clear() {}  // the reference frees 4.6 GB of arena scratch here (:3074-3076); nothing to free
 
