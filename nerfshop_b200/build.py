@@ -16,7 +16,7 @@ SOURCES = ["nsb_kernels.cu", "nsb_host_geometry.cpp"]
 HEADERS = ["nsb_device.cuh", "nsb_tc.cuh", os.path.join("..", "..", "include", "nerfshop_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-shared", "-DNSB_MIN_CTAS=4",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-shared",
 ]
 
 

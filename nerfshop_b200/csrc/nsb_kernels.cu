@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_prepare_rays(const DevFrame f, const ui
 #ifndef NSB_ENC_NL
 #define NSB_ENC_NL 2  // levels per loop iteration (8*NL gathers in flight per thread)
 #endif
-__device__ __forceinline__ void encode_to_a32(tc::TileSmem& s, const DevModel& m, bool valid, V3 pw, uint32_t row) {
+__device__ __forceinline__ void encode_to_a32(uint8_t* a32, const DevModel& m, bool valid, V3 pw, uint32_t row) {
 	constexpr int NL = NSB_ENC_NL;
 #pragma unroll 1
 	for (int g = 0; g < MAX_LEVELS / NL; ++g) {
@@ -115,7 +115,7 @@ __device__ __forceinline__ void encode_to_a32(tc::TileSmem& s, const DevModel& m
 			else encode_levels<NL, 2>(m.levels + NL * g, m.grid, pw.x, pw.y, pw.z, h);
 		}
 		// levels NL*g .. NL*g+NL-1 = fp16 features 2*NL*g ..: NL*4 bytes of this row's k-chunk (NL*g)/4
-		uint8_t* dst = s.a32 + ((NL * g) >> 2) * (tc::ROWS * 16) + row * 16 + ((NL * g) & 3) * 4;
+		uint8_t* dst = a32 + ((NL * g) >> 2) * (tc::ROWS * 16) + row * 16 + ((NL * g) & 3) * 4;
 		if (NL == 2) *reinterpret_cast<uint2*>(dst) = make_uint2(tc::pack_h2(h[0]), tc::pack_h2(h[1]));
 		else *reinterpret_cast<uint4*>(dst) = make_uint4(tc::pack_h2(h[0]), tc::pack_h2(h[1]), tc::pack_h2(h[NL > 2 ? 2 : 0]), tc::pack_h2(h[NL > 3 ? 3 : 0]));
 	}
@@ -131,25 +131,67 @@ __device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__u
 // Per-slot ray state parked in shared memory (SoA: lane-contiguous, conflict-free). Only the acquire and composite phases
 // touch it, so it does not occupy registers while the thread gathers hash-grid features and walks the MLP layers.
 enum { R_OX = 0, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_T, R_CR, R_CG, R_CB, R_CA, R_DEPTH, R_MAXW, R_FIELDS };
-struct RenderSmem {
-	tc::TileSmem tile;
+// One CTA per SM holds NSB_TILES independent tiles (a tile = 128 threads = 128 ray slots = one UMMA M). The tiles share the 20 KB
+// weight image — four separate CTAs would hold four copies — which matters because shared memory is carved out of the same
+// 256 KB as the L1 that serves the hash-grid gathers: 4 x 43.6 KB CTAs leave ~60 KB of L1, one 4-tile CTA (112 KB) leaves ~124 KB
+// (profiles/README.md: the tile loop runs 44 % faster with 92 KB of L1 than with 28 KB).
+#ifndef NSB_TILES
+#define NSB_TILES 4
+#endif
+struct TileBlock {
+	union {
+		uint8_t a64[tc::A64_BYTES];
+		uint8_t a32[tc::A32_BYTES];
+	};
 	float ray[R_FIELDS][128];
+	uint64_t mma_bar;
+	uint64_t pad[15];
 };
+struct __align__(128) RenderSmem {
+	uint8_t w[tc::W_BYTES];
+	TileBlock tile[NSB_TILES];
+	uint64_t w_bar;
+	uint32_t tmem_base;
+	uint32_t pad;
+};
+constexpr uint32_t RENDER_TMEM_COLS = NSB_TILES <= 1 ? 64 : NSB_TILES <= 2 ? 128 : NSB_TILES <= 4 ? 256 : 512;
 
-__global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
+__global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
                                                       float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
                                                       const uint32_t* __restrict__ n_queued_ptr, uint32_t* fetch_counter,
                                                       unsigned long long* __restrict__ stats, const int refill_thr, const int dda_budget) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	RenderSmem& RS = *reinterpret_cast<RenderSmem*>(smem_raw);
-	tc::TileSmem& S = RS.tile;
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = threadIdx.x & 127u;      // slot / row within the tile
+	const uint32_t tile = threadIdx.x >> 7;
+	TileBlock& TB = RS.tile[tile];
 	const uint32_t lane = tid & 31u;
 	const uint32_t n_queued = *n_queued_ptr;
-	if (blockIdx.x * 128u >= n_queued && blockIdx.x > 0) return;  // nothing this CTA could ever fetch
+	if (blockIdx.x * 128u * NSB_TILES >= n_queued && blockIdx.x > 0) return;  // nothing this CTA could ever fetch
 
-	const uint32_t tmem_base = tc::tile_setup(S, m.w_image);
+	// CTA setup: barriers, TMEM (64 columns per tile), one bulk-TMA copy of the weight image
+	if (threadIdx.x == 0) {
+		tc::mbar_init(&RS.w_bar, 1);
+		for (int t = 0; t < NSB_TILES; ++t) tc::mbar_init(&RS.tile[t].mma_bar, 1);
+		tc::fence_mbar_init();
+	}
+	if (threadIdx.x < 32) tc::tmem_alloc(&RS.tmem_base, RENDER_TMEM_COLS);
+	tc::tc_fence_before();
+	__syncthreads();
+	tc::tc_fence_after();
+	if (threadIdx.x < 32) {
+		if (threadIdx.x == 0) {
+			tc::mbar_expect_tx(&RS.w_bar, tc::W_BYTES);
+			tc::bulk_g2s(RS.w, m.w_image, tc::W_BYTES, &RS.w_bar);
+		}
+		__syncwarp();
+	}
+	tc::mbar_wait(&RS.w_bar, 0);
+	const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&RS.tmem_base);
+	tc::TileCtx C;
+	C.a32 = TB.a32; C.a64 = TB.a64; C.w_addr = tc::smem_u32(RS.w); C.mma_bar = &TB.mma_bar; C.tmem = tmem_base + tile * tc::TMEM_COLS; C.row = tid;
+	C.bar_id = 1 + tile;
 
 	const bool ops_on = f.apply_ops && n_ops > 0;
 
@@ -181,7 +223,7 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 	};
 
 	for (;;) {
-		if (!__syncthreads_or((alive || !exhausted) ? 1 : 0)) break;
+		if (!tc::tile_any(C, alive || !exhausted)) break;
 		const long long c0 = clock64();
 
 		// ---- acquire one occupied sample for this thread (refill the ray slot when it is free) ----
@@ -190,9 +232,9 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 		V3 pos = v3(0, 0, 0), dw = v3(0.5f, 0.5f, 0.5f);
 		{
 			int budget = dda_budget;
-			V3 ro = v3(RS.ray[R_OX][tid], RS.ray[R_OY][tid], RS.ray[R_OZ][tid]);
-			V3 rd = v3(RS.ray[R_DX][tid], RS.ray[R_DY][tid], RS.ray[R_DZ][tid]);
-			float t = RS.ray[R_T][tid];
+			V3 ro = v3(TB.ray[R_OX][tid], TB.ray[R_OY][tid], TB.ray[R_OZ][tid]);
+			V3 rd = v3(TB.ray[R_DX][tid], TB.ray[R_DY][tid], TB.ray[R_DZ][tid]);
+			float t = TB.ray[R_T][tid];
 			// Coherent refill: free lanes wait until the warp is down to <= refill_thr live rays and then refill TOGETHER
 			// with consecutive queue entries (= neighbouring pixels), so the lanes of a warp gather from the same few
 			// hash-grid cells on the coarse and middle levels instead of 32 unrelated cache lines per instruction.
@@ -214,10 +256,10 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 					make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
 					ro = r.o; rd = r.d;
 					t = rr.t;
-					RS.ray[R_OX][tid] = ro.x; RS.ray[R_OY][tid] = ro.y; RS.ray[R_OZ][tid] = ro.z;
-					RS.ray[R_DX][tid] = rd.x; RS.ray[R_DY][tid] = rd.y; RS.ray[R_DZ][tid] = rd.z;
-					RS.ray[R_CR][tid] = 0.0f; RS.ray[R_CG][tid] = 0.0f; RS.ray[R_CB][tid] = 0.0f; RS.ray[R_CA][tid] = 0.0f;
-					RS.ray[R_DEPTH][tid] = 0.0f; RS.ray[R_MAXW][tid] = 0.0f;
+					TB.ray[R_OX][tid] = ro.x; TB.ray[R_OY][tid] = ro.y; TB.ray[R_OZ][tid] = ro.z;
+					TB.ray[R_DX][tid] = rd.x; TB.ray[R_DY][tid] = rd.y; TB.ray[R_DZ][tid] = rd.z;
+					TB.ray[R_CR][tid] = 0.0f; TB.ray[R_CG][tid] = 0.0f; TB.ray[R_CB][tid] = 0.0f; TB.ray[R_CA][tid] = 0.0f;
+					TB.ray[R_DEPTH][tid] = 0.0f; TB.ray[R_MAXW][tid] = 0.0f;
 					n_steps = 0;
 					alive = true;
 				}
@@ -226,7 +268,7 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 				const MarchResult mr = next_occupied_budget(f, bitfield, ro, rd, idir, t, dt, pos, budget);
 				if (mr == MARCH_FOUND) { has_sample = true; break; }
 				if (mr == MARCH_EXIT) {
-					finish(true, RS.ray[R_CR][tid], RS.ray[R_CG][tid], RS.ray[R_CB][tid], RS.ray[R_CA][tid], RS.ray[R_DEPTH][tid]);
+					finish(true, TB.ray[R_CR][tid], TB.ray[R_CG][tid], TB.ray[R_CB][tid], TB.ray[R_CA][tid], TB.ray[R_DEPTH][tid]);
 					continue;
 				}
 				break;  // MARCH_PENDING: resume next round
@@ -235,7 +277,7 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 				dw = warp_direction(rd);
 				t = add(t, dt);
 			}
-			if (alive) RS.ray[R_T][tid] = t;
+			if (alive) TB.ray[R_T][tid] = t;
 		}
 
 		// ---- network inputs: generate_next_nerf_network_inputs :690 ----
@@ -267,16 +309,16 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 		float sigma_old_raw = 0.0f;
 		uint32_t dens[8], rgbo[8];
 		int first_pass = 1;
-		if (ops_on && any_poisson && f.poisson_target) first_pass = __syncthreads_or(need_old ? 1 : 0) ? 0 : 1;
+		if (ops_on && any_poisson && f.poisson_target) first_pass = tc::tile_any(C, need_old) ? 0 : 1;
 		const long long c1 = clock64();
 		long long enc_cycles = 0;
 #pragma unroll 1
 		for (int pass = first_pass; pass < 2; ++pass) {
 			const bool old_pass = pass == 0;
 			const long long e0 = clock64();
-			encode_to_a32(S, m, old_pass ? need_old : has_sample, old_pass ? pw_old : pw, tid);
+			encode_to_a32(TB.a32, m, old_pass ? need_old : has_sample, old_pass ? pw_old : pw, tid);
 			enc_cycles += clock64() - e0;
-			tc::run_network(S, tmem_base, phase, dw, old_pass, dens, rgbo);
+			tc::run_network(C, phase, dw, old_pass, dens, rgbo);
 			if (old_pass) {
 				sigma_old_raw = h_lo(dens[0]);
 				if (need_old) ++c_old;
@@ -289,8 +331,8 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 		if (has_sample) {
 			const float sat = 1.0f - f.min_T;  // rendering_min_transmittance test of composite_kernel_nerf :951
 			const V3 cam_fwd = v3(f.cam1[6], f.cam1[7], f.cam1[8]);
-			float cr = RS.ray[R_CR][tid], cg = RS.ray[R_CG][tid], cb = RS.ray[R_CB][tid], ca = RS.ray[R_CA][tid];
-			float ray_depth = RS.ray[R_DEPTH][tid], max_weight = RS.ray[R_MAXW][tid];
+			float cr = TB.ray[R_CR][tid], cg = TB.ray[R_CG][tid], cb = TB.ray[R_CB][tid], ca = TB.ray[R_CA][tid];
+			float ray_depth = TB.ray[R_DEPTH][tid], max_weight = TB.ray[R_MAXW][tid];
 			V3 cpos = unwarp_position(pw, f.tmin, f.tmax);
 			float T = 1.0f - ca;
 			float dtu = unwarp_dt(dtw);
@@ -314,7 +356,7 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 			float weight = alpha * T;
 			float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
 			if (f.mode != NSB_RENDER_SHADE) {
-				const V3 ro = v3(RS.ray[R_OX][tid], RS.ray[R_OY][tid], RS.ray[R_OZ][tid]);
+				const V3 ro = v3(TB.ray[R_OX][tid], TB.ray[R_OY][tid], TB.ray[R_OZ][tid]);
 				if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
 				else if (f.mode == NSB_RENDER_POSITIONS) { rgb[0] = (cpos.x - 0.5f) / 2.0f + 0.5f; rgb[1] = (cpos.y - 0.5f) / 2.0f + 0.5f; rgb[2] = (cpos.z - 0.5f) / 2.0f + 0.5f; }
 				else if (f.mode == NSB_RENDER_DEPTH) { float z = dot3(cam_fwd, vsub(cpos, ro)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
@@ -345,14 +387,16 @@ __global__ void __launch_bounds__(128, NSB_MIN_CTAS) k_render_fused(const DevFra
 				cr = __fdiv_rn(cr, a); cg = __fdiv_rn(cg, a); cb = __fdiv_rn(cb, a); ca = __fdiv_rn(ca, a);
 				finish(false, cr, cg, cb, ca, ray_depth);
 			} else {
-				RS.ray[R_CR][tid] = cr; RS.ray[R_CG][tid] = cg; RS.ray[R_CB][tid] = cb; RS.ray[R_CA][tid] = ca;
-				RS.ray[R_DEPTH][tid] = ray_depth; RS.ray[R_MAXW][tid] = max_weight;
+				TB.ray[R_CR][tid] = cr; TB.ray[R_CG][tid] = cg; TB.ray[R_CB][tid] = cb; TB.ray[R_CA][tid] = ca;
+				TB.ray[R_DEPTH][tid] = ray_depth; TB.ray[R_MAXW][tid] = max_weight;
 			}
 		}
 		cyc_acq += c1 - c0; cyc_enc += c2 - c1; cyc_mlp += c3 - c2; cyc_comp += clock64() - c3; ++n_rounds;
 	}
 
-	tc::tile_teardown(S, tmem_base);
+	tc::tc_fence_before();
+	__syncthreads();  // all tiles done
+	if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, RENDER_TMEM_COLS);
 	if (tid == 0) {
 		atomicAdd(stats + ST_ROUNDS, (unsigned long long)n_rounds);
 		atomicAdd(stats + ST_CYC_ACQUIRE, (unsigned long long)cyc_acq);
@@ -395,8 +439,8 @@ __global__ void __launch_bounds__(128) k_inference(const DevModel m, const float
 			dw = v3(coords[7 * (size_t)i + 4], coords[7 * (size_t)i + 5], coords[7 * (size_t)i + 6]);
 		}
 		uint32_t dens[8], rgbo[8];
-		encode_to_a32(S, m, valid, pw, tid);
-		tc::run_network(S, tmem_base, phase, dw, DENSITY_ONLY, dens, rgbo);
+		encode_to_a32(S.a32, m, valid, pw, tid);
+		tc::run_network(tc::single_tile_ctx(S, tmem_base), phase, dw, DENSITY_ONLY, dens, rgbo);
 		if (i < n_padded) {
 			const uint32_t* src = DENSITY_ONLY ? dens : rgbo;
 #pragma unroll
@@ -570,8 +614,8 @@ __global__ void __launch_bounds__(128) k_density_grid_update(const DevModel m, c
 			}
 		}
 		uint32_t dens[8], rgbo[8];
-		encode_to_a32(S, m, valid, pw, tid);
-		tc::run_network(S, tmem_base, phase, dw, true, dens, rgbo);
+		encode_to_a32(S.a32, m, valid, pw, tid);
+		tc::run_network(tc::single_tile_ctx(S, tmem_base), phase, dw, true, dens, rgbo);
 		if (valid) {
 			__half h = __float2half_rn(network_to_density(__half2float(__ushort_as_half((unsigned short)(dens[0] & 0xffffu))), a.density_activation));
 			if (a.apply_ops) {
@@ -832,47 +876,46 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	CU(cudaEventCreate(&c->ev1));
 	CU(cudaEventCreate(&c->evm));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RenderSmem)));
-	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
-	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
-	CU(cudaFuncSetAttribute(k_density_grid_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc::TileSmem)));
-	CU(cudaFuncSetAttribute(k_density_grid_update, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	// Persistent grid = SMs x resident CTAs. Residency is bounded by registers (128/thread -> 4), shared memory
-	// (45 KB -> 5 of 227 KB; the carve-out is requested explicitly, the default heuristic picks a small one) and
-	// TMEM (64 of 512 columns per CTA -> 8).
-	CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	CU(cudaFuncSetAttribute(k_inference<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	CU(cudaFuncSetAttribute(k_inference<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	int occ = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_render_fused, 128, sizeof(RenderSmem)));
+	// Shared memory and L1 share one 256 KB array per SM: every kernel asks for exactly the carve-out its resident CTAs need and
+	// leaves the rest to L1, which serves the hash-grid gathers (the default heuristic picks a carve-out too small for even one
+	// CTA; "max shared" starves L1 — the tile loop runs 44 % faster with 92 KB of L1 than with 28 KB, profiles/README.md).
+	auto set_smem = [&](const void* func, size_t bytes_per_cta, int ctas) -> cudaError_t {
+		cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_per_cta);
+		if (e != cudaSuccess) return e;
+		const size_t need = (bytes_per_cta + 1024) * (size_t)ctas;  // 1 KB per CTA is reserved by the system
+		int pct = (int)((need * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor);
+		if (pct > 100) pct = 100;
+		return cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+	};
+	// k_render_fused: ONE CTA of NSB_TILES tiles per SM (512 threads x 128 registers = the whole register file; TMEM 64 columns
+	// per tile; shared memory 20 KB weights + 23 KB per tile).
+	c->ctas_per_sm = 1;
+	CU(set_smem((const void*)k_render_fused, sizeof(RenderSmem), 1));
 	cudaFuncAttributes fa;
 	CU(cudaFuncGetAttributes(&fa, k_render_fused));
-	int by_regs = fa.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fa.numRegs * 128)) : 4;
-	int by_smem = (int)(prop.sharedMemPerMultiprocessor / (sizeof(RenderSmem) + 1024));
 	const int by_smem_tile = (int)(prop.sharedMemPerMultiprocessor / (sizeof(tc::TileSmem) + 1024));
-	int want = by_regs < by_smem ? by_regs : by_smem;
-	if (want > 8) want = 8;
-	if (want < 1) want = 1;
-	c->ctas_per_sm = want;
-	{   // the operator-level inference kernel is lighter (no ray state): its own residency
+	{   // the operator-level kernels: one tile per CTA, residency from registers / shared memory
 		cudaFuncAttributes fi;
 		CU(cudaFuncGetAttributes(&fi, k_inference<false>));
 		int r = fi.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fi.numRegs * 128)) : 4;
 		c->inference_ctas_per_sm = r < by_smem_tile ? r : by_smem_tile;
-		if (c->inference_ctas_per_sm > 8) c->inference_ctas_per_sm = 8;
+		if (c->inference_ctas_per_sm > 5) c->inference_ctas_per_sm = 5;
 		if (c->inference_ctas_per_sm < 1) c->inference_ctas_per_sm = 1;
 		CU(cudaFuncGetAttributes(&fi, k_density_grid_update));
 		r = fi.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fi.numRegs * 128)) : 4;
 		c->grid_update_ctas_per_sm = r < by_smem_tile ? r : by_smem_tile;
-		if (c->grid_update_ctas_per_sm > 8) c->grid_update_ctas_per_sm = 8;
+		if (c->grid_update_ctas_per_sm > 5) c->grid_update_ctas_per_sm = 5;
 		if (c->grid_update_ctas_per_sm < 1) c->grid_update_ctas_per_sm = 1;
+		CU(set_smem((const void*)k_inference<false>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
+		CU(set_smem((const void*)k_inference<true>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
+		CU(set_smem((const void*)k_density_grid_update, sizeof(tc::TileSmem), c->grid_update_ctas_per_sm));
 	}
-	if (const char* e = getenv("NSB_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) c->ctas_per_sm = v; }
+	if (const char* e = getenv("NSB_CARVEOUT")) CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));  // experiments
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
 	if (getenv("NSB_VERBOSE"))
-		fprintf(stderr, "[nsb] device %d: %d SMs, occupancy API %d, regs %d -> %d, smem %zu -> %d, using %d CTAs/SM\n", device, c->sm_count, occ, fa.numRegs, by_regs,
-		        sizeof(RenderSmem), by_smem, c->ctas_per_sm);
+		fprintf(stderr, "[nsb] device %d: %d SMs; k_render_fused %d tiles/CTA, %d regs, %zu B smem; inference %d CTAs/SM, grid update %d CTAs/SM\n", device, c->sm_count,
+		        NSB_TILES, fa.numRegs, sizeof(RenderSmem), c->inference_ctas_per_sm, c->grid_update_ctas_per_sm);
 	*out = c;
 	return NSB_OK;
 }
@@ -1465,8 +1508,8 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(c->evm, stream));
 		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
-		if (grid > my_tiles) grid = my_tiles;
-		k_render_fused<<<grid, 128, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
+		if (grid > (my_tiles + NSB_TILES - 1) / NSB_TILES) grid = (uint32_t)((my_tiles + NSB_TILES - 1) / NSB_TILES);
+		k_render_fused<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
 		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
 		                                                          c->refill_thr, c->dda_budget);
 		CU(cudaGetLastError());

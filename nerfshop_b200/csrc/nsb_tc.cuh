@@ -164,14 +164,39 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, ui
 // waits on the mbarrier: if lanes 1-31 reached mbarrier.try_wait first (divergent from lane 0), the warp would
 // sleep in the hardware wait until its time-out before lane 0 ever issued the instruction it is waiting for.
 template <uint32_t N, uint32_t K>
-__device__ __forceinline__ void issue_converged(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
-	if (threadIdx.x < 32) {
-		if (threadIdx.x == 0) {
+__device__ __forceinline__ void issue_converged(uint32_t row, uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
+	if (row < 32) {  // warp 0 of the tile
+		if (row == 0) {
 			tc_fence_after();
 			issue_layer<N, K>(tmem_d, a_addr, w_addr, bar);
 		}
 		__syncwarp();
 	}
+}
+
+// ---- a tile = 128 threads (4 warps, TMEM lanes 0-127) walking the layer chain together. A CTA may hold several tiles
+// (they share the weight image; each has its own operands, mbarrier, TMEM columns and named barrier).
+struct TileCtx {
+	uint8_t* a32;        // 32-wide operand (aliases the first half of a64)
+	uint8_t* a64;
+	uint32_t w_addr;     // shared-window address of the weight image
+	uint64_t* mma_bar;
+	uint32_t tmem;       // TMEM address of this tile's column 0, lane 0
+	uint32_t row;        // 0..127 within the tile
+	uint32_t bar_id;     // named barrier of the tile (0 = the CTA barrier when the CTA is one tile)
+};
+__device__ __forceinline__ void tile_sync(const TileCtx& c) { asm volatile("bar.sync %0, 128;" ::"r"(c.bar_id) : "memory"); }
+__device__ __forceinline__ bool tile_any(const TileCtx& c, bool p) {
+	uint32_t r;
+	asm volatile(
+		"{\n\t.reg .pred p, q;\n\t"
+		"setp.ne.u32 q, %2, 0;\n\t"
+		"barrier.cta.red.or.pred p, %1, 128, q;\n\t"
+		"selp.u32 %0, 1, 0, p;\n\t}"
+		: "=r"(r)
+		: "r"(c.bar_id), "r"((uint32_t)p)
+		: "memory");
+	return r != 0;
 }
 
 // ---- tile lifecycle -------------------------------------------------------------------------------
@@ -218,7 +243,7 @@ __device__ __forceinline__ uint32_t pack(uint32_t a_bits, uint32_t b_bits) {
 }
 
 // Epilogue of a 64-wide hidden layer: TMEM fp32 [row][0..63] -> ReLU -> fp16 -> a64 row (8 chunks)
-__device__ __forceinline__ void epilogue_hidden(TileSmem& s, uint32_t tmem_row, uint32_t row) {
+__device__ __forceinline__ void epilogue_hidden(uint8_t* a64, uint32_t tmem_row, uint32_t row) {
 #pragma unroll
 	for (uint32_t q = 0; q < 2; ++q) {
 		uint32_t r[32];
@@ -229,39 +254,31 @@ __device__ __forceinline__ void epilogue_hidden(TileSmem& s, uint32_t tmem_row, 
 		for (uint32_t j = 0; j < 4; ++j) {
 			uint4 c = make_uint4(relu_pack(r[8 * j + 0], r[8 * j + 1]), relu_pack(r[8 * j + 2], r[8 * j + 3]), relu_pack(r[8 * j + 4], r[8 * j + 5]),
 			                     relu_pack(r[8 * j + 6], r[8 * j + 7]));
-			store_chunk(s.a64, 4 * q + j, row, c);
+			store_chunk(a64, 4 * q + j, row, c);
 		}
 	}
 }
 
-// Runs the network on the 128 rows whose grid features are already in s.a32 (chunks 0-3).
+// Runs the network on the tile's 128 rows whose grid features are already in c.a32 (chunks 0-3).
 //   density_only: stop after L2 (NerfNetwork::density)
 //   dens[8]: the 16 fp16 outputs of the density MLP (packed half2), rgb[8]: the 16 outputs of the rgb MLP.
 // `dw` = this row's warped view direction; its 16 SH values are evaluated between L2 and L3.
-// `phase` is the running parity of s.mma_bar (one flip per layer).
-__device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uint32_t& phase, V3 dw, bool density_only,
-                                            uint32_t* dens, uint32_t* rgb) {
-	const uint32_t tid = threadIdx.x;
-	const uint32_t row = tid;
-	const uint32_t tmem_row = tmem_base + ((tid & ~31u) << 16);  // lane field = first lane of this warp's quarter
-	const uint32_t a32 = smem_u32(s.a32), a64 = smem_u32(s.a64), w = smem_u32(s.w);
-
-	// ---- L1: a32 (32) -> 64
-	fence_async_smem();
-	tc_fence_before();
-	__syncthreads();
-	issue_converged<64, 32>(tmem_base, a32, w + W1_OFF, &s.mma_bar);
-	mbar_wait(&s.mma_bar, phase); phase ^= 1;
+// `phase` is the running parity of the tile's mma_bar (one flip per layer).
+__device__ __forceinline__ void run_network(const TileCtx& c, uint32_t& phase, V3 dw, bool density_only, uint32_t* dens, uint32_t* rgb) {
+	const uint32_t row = c.row;
+	const uint32_t tmem_row = c.tmem + ((row & ~31u) << 16);  // lane field = first lane of this warp's quarter
+	const uint32_t a32 = smem_u32(c.a32), a64 = smem_u32(c.a64), w = c.w_addr;
+#define NSB_SYNC_ISSUE(N_, K_, A_, W_)                                  \
+	fence_async_smem();                                                 \
+	tc_fence_before();                                                  \
+	tile_sync(c);                                                       \
+	issue_converged<N_, K_>(row, c.tmem, A_, w + W_, c.mma_bar);        \
+	mbar_wait(c.mma_bar, phase); phase ^= 1;                            \
 	tc_fence_after();
-	epilogue_hidden(s, tmem_row, row);
 
-	// ---- L2: a64 (64) -> 16
-	fence_async_smem();
-	tc_fence_before();
-	__syncthreads();
-	issue_converged<16, 64>(tmem_base, a64, w + W2_OFF, &s.mma_bar);
-	mbar_wait(&s.mma_bar, phase); phase ^= 1;
-	tc_fence_after();
+	NSB_SYNC_ISSUE(64, 32, a32, W1_OFF)   // L1: a32 (32) -> 64
+	epilogue_hidden(c.a64, tmem_row, row);
+	NSB_SYNC_ISSUE(16, 64, a64, W2_OFF)   // L2: a64 (64) -> 16
 	{
 		uint32_t r[16];
 		tmem_ld16(tmem_row, r);
@@ -273,36 +290,15 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 	// rgb-network input: rows 0-15 = density MLP output, 16-31 = SH (nerf_network_full.h:52,67,79)
 	__half2 sh[8];
 	encode_sh4(dw, sh);  // tcnn SphericalHarmonics of the (mapped) direction: rows 16-31 of the rgb network input
-	store_chunk(s.a32, 0, row, make_uint4(dens[0], dens[1], dens[2], dens[3]));
-	store_chunk(s.a32, 1, row, make_uint4(dens[4], dens[5], dens[6], dens[7]));
-	store_chunk(s.a32, 2, row, make_uint4(pack_h2(sh[0]), pack_h2(sh[1]), pack_h2(sh[2]), pack_h2(sh[3])));
-	store_chunk(s.a32, 3, row, make_uint4(pack_h2(sh[4]), pack_h2(sh[5]), pack_h2(sh[6]), pack_h2(sh[7])));
-
-	// ---- L3: a32 -> 64
-	fence_async_smem();
-	tc_fence_before();
-	__syncthreads();
-	issue_converged<64, 32>(tmem_base, a32, w + W3_OFF, &s.mma_bar);
-	mbar_wait(&s.mma_bar, phase); phase ^= 1;
-	tc_fence_after();
-	epilogue_hidden(s, tmem_row, row);
-
-	// ---- L4: a64 -> 64
-	fence_async_smem();
-	tc_fence_before();
-	__syncthreads();
-	issue_converged<64, 64>(tmem_base, a64, w + W4_OFF, &s.mma_bar);
-	mbar_wait(&s.mma_bar, phase); phase ^= 1;
-	tc_fence_after();
-	epilogue_hidden(s, tmem_row, row);
-
-	// ---- L5: a64 -> 16
-	fence_async_smem();
-	tc_fence_before();
-	__syncthreads();
-	issue_converged<16, 64>(tmem_base, a64, w + W5_OFF, &s.mma_bar);
-	mbar_wait(&s.mma_bar, phase); phase ^= 1;
-	tc_fence_after();
+	store_chunk(c.a32, 0, row, make_uint4(dens[0], dens[1], dens[2], dens[3]));
+	store_chunk(c.a32, 1, row, make_uint4(dens[4], dens[5], dens[6], dens[7]));
+	store_chunk(c.a32, 2, row, make_uint4(pack_h2(sh[0]), pack_h2(sh[1]), pack_h2(sh[2]), pack_h2(sh[3])));
+	store_chunk(c.a32, 3, row, make_uint4(pack_h2(sh[4]), pack_h2(sh[5]), pack_h2(sh[6]), pack_h2(sh[7])));
+	NSB_SYNC_ISSUE(64, 32, a32, W3_OFF)   // L3: a32 -> 64
+	epilogue_hidden(c.a64, tmem_row, row);
+	NSB_SYNC_ISSUE(64, 64, a64, W4_OFF)   // L4: a64 -> 64
+	epilogue_hidden(c.a64, tmem_row, row);
+	NSB_SYNC_ISSUE(16, 64, a64, W5_OFF)   // L5: a64 -> 16
 	{
 		uint32_t r[16];
 		tmem_ld16(tmem_row, r);
@@ -311,6 +307,12 @@ __device__ __forceinline__ void run_network(TileSmem& s, uint32_t tmem_base, uin
 		for (int i = 0; i < 8; ++i) rgb[i] = pack(r[2 * i], r[2 * i + 1]);
 	}
 	tc_fence_before();
+#undef NSB_SYNC_ISSUE
+}
+__device__ __forceinline__ TileCtx single_tile_ctx(TileSmem& s, uint32_t tmem_base) {
+	TileCtx c;
+	c.a32 = s.a32; c.a64 = s.a64; c.w_addr = smem_u32(s.w); c.mma_bar = &s.mma_bar; c.tmem = tmem_base; c.row = threadIdx.x; c.bar_id = 0;
+	return c;
 }
 
 }  // namespace tc
