@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	const bool ops_on = f.apply_ops && n_ops > 0;
 
 	// what stays in registers across a round
-	bool alive = false, exhausted = false;
+	bool alive = false, exhausted = false;  // exhausted is warp-uniform: the queue had nothing left when this warp last asked
+	uint32_t ch_next = 0, ch_end = 0;       // this warp's chunk of the ray queue (warp-uniform)
 	uint32_t pix = 0, n_steps = 0;
 	uint32_t c_hit = 0, c_samples = 0, c_old = 0;
 	uint32_t phase = 0;
@@ -235,34 +236,49 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 			V3 ro = v3(TB.ray[R_OX][tid], TB.ray[R_OY][tid], TB.ray[R_OZ][tid]);
 			V3 rd = v3(TB.ray[R_DX][tid], TB.ray[R_DY][tid], TB.ray[R_DZ][tid]);
 			float t = TB.ray[R_T][tid];
-			// Coherent refill: free lanes wait until the warp is down to <= refill_thr live rays and then refill TOGETHER
-			// with consecutive queue entries (= neighbouring pixels), so the lanes of a warp gather from the same few
-			// hash-grid cells on the coarse and middle levels instead of 32 unrelated cache lines per instruction.
-			const bool may_refill = __popc(__ballot_sync(0xffffffffu, alive)) <= refill_thr;
-			for (;;) {
-				if (!alive) {
-					if (exhausted || !may_refill) break;
-					// warp-aggregated fetch: the lanes that need a ray right now take consecutive queue entries
-					const unsigned grp = __activemask();
-					const int leader = __ffs(grp) - 1;
-					uint32_t base = 0;
-					if ((int)lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(grp));
-					base = __shfl_sync(grp, base, leader);
-					const uint32_t qi = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-					if (qi >= n_queued) { exhausted = true; break; }
-					const RayRec rr = list[qi];
-					pix = rr.pix;
-					Ray r;
-					make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
-					ro = r.o; rd = r.d;
-					t = rr.t;
-					TB.ray[R_OX][tid] = ro.x; TB.ray[R_OY][tid] = ro.y; TB.ray[R_OZ][tid] = ro.z;
-					TB.ray[R_DX][tid] = rd.x; TB.ray[R_DY][tid] = rd.y; TB.ray[R_DZ][tid] = rd.z;
-					TB.ray[R_CR][tid] = 0.0f; TB.ray[R_CG][tid] = 0.0f; TB.ray[R_CB][tid] = 0.0f; TB.ray[R_CA][tid] = 0.0f;
-					TB.ray[R_DEPTH][tid] = 0.0f; TB.ray[R_MAXW][tid] = 0.0f;
-					n_steps = 0;
-					alive = true;
+			// Refill (warp-convergent). Free lanes wait until the warp is down to <= refill_thr live rays; rays come from a queue CHUNK
+			// this warp owns (consecutive entries = neighbouring pixels), so the lanes of a warp gather from the same few hash-grid
+			// cells on the coarse and middle levels instead of 32 unrelated cache lines per instruction.
+			{
+				const unsigned alive_m = __ballot_sync(0xffffffffu, alive);
+				const unsigned want = exhausted ? 0u : ~alive_m;
+				if (want && __popc(alive_m) <= (refill_thr & 0xff)) {
+					const uint32_t need = (uint32_t)__popc(want), rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
+					const uint32_t chunk = (uint32_t)refill_thr >> 8;
+					uint32_t given = 0, qi = 0xffffffffu;
+					while (given < need) {  // warp-uniform
+						if (ch_next >= ch_end) {
+							const uint32_t claim = chunk ? chunk : need - given;
+							uint32_t base = 0;
+							if (lane == 0) base = atomicAdd(fetch_counter, claim);
+							base = __shfl_sync(0xffffffffu, base, 0);
+							if (base >= n_queued) { exhausted = true; break; }
+							ch_next = base;
+							ch_end = min(base + claim, n_queued);
+						}
+						const uint32_t take = min(need - given, ch_end - ch_next);
+						if (!alive && rank >= given && rank < given + take) qi = ch_next + (rank - given);
+						ch_next += take;
+						given += take;
+					}
+					if (qi != 0xffffffffu) {
+						const RayRec rr = list[qi];
+						pix = rr.pix;
+						Ray r;
+						make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
+						ro = r.o; rd = r.d;
+						t = rr.t;
+						TB.ray[R_OX][tid] = ro.x; TB.ray[R_OY][tid] = ro.y; TB.ray[R_OZ][tid] = ro.z;
+						TB.ray[R_DX][tid] = rd.x; TB.ray[R_DY][tid] = rd.y; TB.ray[R_DZ][tid] = rd.z;
+						TB.ray[R_CR][tid] = 0.0f; TB.ray[R_CG][tid] = 0.0f; TB.ray[R_CB][tid] = 0.0f; TB.ray[R_CA][tid] = 0.0f;
+						TB.ray[R_DEPTH][tid] = 0.0f; TB.ray[R_MAXW][tid] = 0.0f;
+						n_steps = 0;
+						alive = true;
+					}
 				}
+			}
+			for (;;) {
+				if (!alive) break;
 				if (n_steps >= MARCH_ITER - 1) { alive = false; continue; }  // still marching after MARCH_ITER steps: dropped (:2812)
 				const V3 idir = v3(div_(1.0f, rd.x), div_(1.0f, rd.y), div_(1.0f, rd.z));
 				const MarchResult mr = next_occupied_budget(f, bitfield, ro, rd, idir, t, dt, pos, budget);
@@ -912,6 +928,7 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	}
 	if (const char* e = getenv("NSB_CARVEOUT")) CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));  // experiments
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
+	if (const char* e = getenv("NSB_CHUNK")) { int v = atoi(e); if (v >= 0 && v <= 65535) c->refill_thr |= v << 8; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
 	if (getenv("NSB_VERBOSE"))
 		fprintf(stderr, "[nsb] device %d: %d SMs; k_render_fused %d tiles/CTA, %d regs, %zu B smem; inference %d CTAs/SM, grid update %d CTAs/SM\n", device, c->sm_count,
