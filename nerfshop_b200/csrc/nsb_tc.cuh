@@ -234,9 +234,10 @@ __device__ __forceinline__ void store_chunk(uint8_t* base, uint32_t chunk, uint3
 	*reinterpret_cast<uint4*>(base + chunk * (ROWS * 16) + row * 16) = v;
 }
 __device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// ReLU after the fp16 conversion: rounding is monotone and 0 is exact, so max(cvt(x), 0) == cvt(max(x, 0)) — one packed
+// HMNMX2 per pair instead of two FMNMX.
 __device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits) {
-	float a = fmaxf(__uint_as_float(a_bits), 0.0f), b = fmaxf(__uint_as_float(b_bits), 0.0f);
-	return pack_h2(__floats2half2_rn(a, b));
+	return pack_h2(__hmax2(__floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits)), __floats2half2_rn(0.0f, 0.0f)));
 }
 __device__ __forceinline__ uint32_t pack(uint32_t a_bits, uint32_t b_bits) {
 	return pack_h2(__floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits)));
