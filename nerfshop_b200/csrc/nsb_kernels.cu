@@ -3,7 +3,7 @@
 // The product kernel is k_render_fused: ONE persistent launch per frame that replaces the reference's
 // per-round pipeline (compact -> generate inputs -> [residuals] -> inference -> [map_rays] -> inference ->
 // composite, >= 12 launches + 3 host syncs per round, testbed_nerf.cu:2812-2990) and its 4.6 GB of
-// scratch: ray state lives in registers, samples go march -> deform -> hash encode -> tcgen05 MLP ->
+// scratch: ray state lives in registers and shared memory, samples go march -> deform -> hash encode -> tcgen05 MLP ->
 // composite without touching HBM, and finished rays are shaded straight into the framebuffer.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -22,10 +22,6 @@
 #include "nsb_tc.cuh"
 
 using namespace nsb;
-
-#ifndef NSB_MIN_CTAS
-#define NSB_MIN_CTAS 3  // resident CTAs per SM the fused kernel is compiled for (register cap = 65536 / (128 * NSB_MIN_CTAS))
-#endif
 
 // =====================================================================================================
 // fused persistent renderer
@@ -124,10 +120,10 @@ __device__ __forceinline__ void encode_to_a32(uint8_t* a32, const DevModel& m, b
 __device__ __forceinline__ float h_lo(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed & 0xffffu))); }
 __device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed >> 16))); }
 
-// Stage 2 (persistent, 128 threads = 128 ray slots = 128 MMA rows per CTA): every round each live ray contributes
+// Stage 2 (persistent; a tile = 128 threads = 128 ray slots = 128 MMA rows, NSB_TILES tiles per CTA): every round each live ray contributes
 // ONE sample; samples go deform -> hash encode -> tcgen05 MLPs -> composite inside the SM; a finished ray is shaded
-// into the framebuffer and its slot refilled from the queue (warp-aggregated fetch, so rays that were refilled
-// together — neighbouring pixels that die on the same surface — stay together in a warp).
+// into the framebuffer and its slot refilled from the queue (warp-convergent fetch of consecutive entries, so rays that
+// were refilled together — neighbouring pixels that die on the same surface — stay together in a warp).
 // Per-slot ray state parked in shared memory (SoA: lane-contiguous, conflict-free). Only the acquire and composite phases
 // touch it, so it does not occupy registers while the thread gathers hash-grid features and walks the MLP layers.
 enum { R_OX = 0, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_T, R_CR, R_CG, R_CB, R_CA, R_DEPTH, R_MAXW, R_FIELDS };

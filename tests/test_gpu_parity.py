@@ -263,3 +263,24 @@ def test_unit_cube_scene_constant_step(renderer, built_lib):
         assert r.stats().n_samples == st_o.n_samples
     finally:
         r.close()
+
+
+def test_empty_and_tiny_frames(scene, oracle, renderer):
+    """No ray enters the AABB (camera outside, looking away): nothing is queued, the framebuffer keeps its content and depth is
+    1e10 everywhere; 1x1 / 3x2 / 16x8 (exactly one tile) frames match the oracle."""
+    import torch
+
+    model, _ = scene
+    away = syn.look_at((6.0, 6.0, 6.0), target=(12.0, 12.0, 12.0))
+    f = syn.make_frame(model, away, 64, 36)
+    bg = torch.full((36, 64, 4), 0.125, device="cuda")
+    fb, depth = renderer.render(f, fb=bg.clone())
+    st = renderer.stats()
+    assert torch.equal(fb, bg) and bool((depth == 1e10).all())
+    assert st.n_rays == 64 * 36 and st.n_rays_alive == 0 and st.n_samples == 0 and st.n_hit == 0
+    for (w, h) in ((1, 1), (3, 2), (16, 8)):
+        f = syn.make_frame(model, syn.fox_camera0(), w, h)
+        fb_o, depth_o, st_o, margin = oracle.render(f, want_margin=True)
+        fb, depth = renderer.render(f)
+        assert np.abs(fb.cpu().numpy() - fb_o).max() <= RGBA_TOL or (margin <= MARGIN_EPS).any()
+        assert renderer.stats().n_samples == st_o.n_samples
