@@ -808,6 +808,7 @@ struct NsbContext {
 		nsb::rebuild::Mark* d_marks = nullptr; uint32_t marks_cap = 0; unsigned int* d_n_marks = nullptr;
 		uint32_t* d_idx = nullptr; uint64_t idx_cap = 0;   // owned replacement of the uploaded tet_lut_idx once it had to grow
 		float* d_boxes = nullptr;      // [12] bbox min/max, warped min/max; [12..17] scene aabb
+		float* d_gamma = nullptr; float* d_mem_small = nullptr; uint32_t mem_n_cv = 0;  // nsb_cage_set_membrane scratch
 		uint64_t n_idx = 0;
 	};
 	std::vector<CageRebuild> rb;
@@ -938,7 +939,7 @@ static void free_ops(NsbContext* c) {
 	c->op_allocs.clear();
 	for (auto& r : c->rb) {
 		cudaFree(r.d_mvc); cudaFree(r.d_cage); cudaFree(r.d_counts); cudaFree(r.d_block_sums); cudaFree(r.d_total); cudaFree(r.d_marks);
-		cudaFree(r.d_n_marks); cudaFree(r.d_idx); cudaFree(r.d_boxes);
+		cudaFree(r.d_n_marks); cudaFree(r.d_idx); cudaFree(r.d_boxes); cudaFree(r.d_gamma); cudaFree(r.d_mem_small);
 	}
 	c->rb.clear();
 	c->h_ops.clear();
@@ -1382,10 +1383,16 @@ extern "C" NsbStatus nsb_cage_set_membrane(NsbContext* c, int32_t op_index, cons
 	memcpy(pack.data() + 3 * (size_t)n_cv, outside_density, n_cv * 4);
 	memcpy(pack.data() + 4 * (size_t)n_cv, inside_shs, (size_t)n_cv * 27 * 4);
 	memcpy(pack.data() + 31 * (size_t)n_cv, outside_shs, (size_t)n_cv * 27 * 4);
-	CU(cudaMalloc(&d_gamma, (size_t)nv * n_cv * 4));
-	c->op_allocs.push_back(d_gamma);  // released with the operator list
-	CU(cudaMalloc(&d_small, small * 4));
-	c->op_allocs.push_back(d_small);
+	auto& r = c->rb[op_index];
+	if (r.mem_n_cv != n_cv) {  // scratch of the blend, kept with the operator (a host re-blends after every boundary re-sampling)
+		cudaFree(r.d_gamma); cudaFree(r.d_mem_small);
+		r.d_gamma = r.d_mem_small = nullptr;
+		CU(cudaMalloc(&r.d_gamma, (size_t)nv * n_cv * 4));
+		CU(cudaMalloc(&r.d_mem_small, small * 4));
+		r.mem_n_cv = n_cv;
+	}
+	d_gamma = r.d_gamma;
+	d_small = r.d_mem_small;
 	CU(cudaMemcpy(d_gamma, gamma, (size_t)nv * n_cv * 4, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(d_small, pack.data(), small * 4, cudaMemcpyHostToDevice));
 	if (!d.shs) { void* q; CU(cudaMalloc(&q, (size_t)nv * 27 * 4)); c->op_allocs.push_back(q); d.shs = (const float*)q; }
