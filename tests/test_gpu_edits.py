@@ -79,3 +79,23 @@ def test_render_with_cage_edits(edited, renderer, fixture, poisson_target):
     renderer.reset_edit_operators()
     b, _ = renderer.render(f0)
     assert (a == b).all()
+
+
+def test_edited_frames_match_golden(edited, renderer):
+    """The committed pins of configs 2-3 (tests/golden/synthetic_edits.npz): one cage, three cages + membrane, and the
+    poisson-target blend, 96x54."""
+    import os
+
+    model, occ = edited
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synthetic_edits.npz"))
+    for name, fixture, target in (("e1", fx.e1(model), False), ("e3", fx.e3(model), False), ("e3_target", fx.e3(model), True)):
+        renderer.set_edit_operators([o.to_op() for o in fixture])
+        f = syn.make_frame(model, syn.fox_camera0(), 96, 54, apply_operators=True, poisson_target=target)
+        fb, depth = renderer.render(f)
+        st = renderer.stats()
+        _compare_frames(fb.cpu().numpy(), depth.cpu().numpy(), g[f"{name}_rgba"], g[f"{name}_depth"], g[f"{name}_margin"])
+        assert [st.n_rays, st.n_rays_alive, st.n_samples] == [int(g[f"{name}_stats"][k]) for k in (0, 1, 3)]
+    ops = [o.to_op() for o in fx.e3(model)]
+    renderer.set_edit_operators(ops)
+    got, mask = renderer.map_rays(g["map_in"])
+    assert np.array_equal(got.view(np.uint32), g["map_out"].view(np.uint32)) and np.array_equal(mask, g["map_mask"])
