@@ -36,15 +36,19 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
     prog = tmp_path / "sz.c"
     prog.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "nerfshop_b200.h"\n'
-        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(NsbModelDesc), sizeof(NsbFrame), sizeof(NsbEditOp), sizeof(NsbAffineBox),"
-        " sizeof(NsbRenderStats), offsetof(NsbFrame, tile_rank), offsetof(NsbEditOp, selection_box), offsetof(NsbEditOp, tet_lut_offsets));return 0;}\n"
+        "int main(){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(NsbModelDesc), sizeof(NsbFrame), sizeof(NsbEditOp), sizeof(NsbAffineBox),"
+        " sizeof(NsbRenderStats), offsetof(NsbFrame, tile_rank), offsetof(NsbEditOp, selection_box), offsetof(NsbEditOp, tet_lut_offsets),"
+        " sizeof(NsbGridUpdate), offsetof(NsbGridUpdate, rng_state), offsetof(NsbGridUpdate, apply_operators), sizeof(NsbBoundarySampling),"
+        " offsetof(NsbBoundarySampling, seed), sizeof(NsbTonemap));return 0;}\n"
     )
     exe = tmp_path / "sz"
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([cc, "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(abi.NsbModelDesc), C.sizeof(abi.NsbFrame), C.sizeof(abi.NsbEditOp), C.sizeof(abi.NsbAffineBox), C.sizeof(abi.NsbRenderStats),
-            abi.NsbFrame.tile_rank.offset, abi.NsbEditOp.selection_box.offset, abi.NsbEditOp.tet_lut_offsets.offset]
+            abi.NsbFrame.tile_rank.offset, abi.NsbEditOp.selection_box.offset, abi.NsbEditOp.tet_lut_offsets.offset,
+            C.sizeof(abi.NsbGridUpdate), abi.NsbGridUpdate.rng_state.offset, abi.NsbGridUpdate.apply_operators.offset, C.sizeof(abi.NsbBoundarySampling),
+            abi.NsbBoundarySampling.seed.offset, C.sizeof(abi.NsbTonemap)]
     assert got == want
 
 
