@@ -3,7 +3,8 @@
   n_params, params_type ("__half"), params_binary   <- tcnn::Trainer::serialize (external; schema as described in SURVEY
                                                        Appendix B — not verifiable in this tree)
   density_grid_size (128), density_grid_binary (float32[5*128^3]), training_step, loss, nerf.{rgb, dataset}
-The render path needs three things from it: the parameter block (nsb_upload_model), the density grid
+`.ingp` files are the same msgpack stream behind zstr (zlib with a gzip wrapper, `testbed.cu:168-171,3173-3176`; zstr reads plain data
+through unchanged). The render path needs three things from it: the parameter block (nsb_upload_model), the density grid
 (nsb_upload_density_grid -> occupancy bitfield) and aabb_scale (render/train AABB, cone angle, per_level_scale).
 """
 from __future__ import annotations
@@ -25,7 +26,7 @@ _BASE_CONFIG = {
 
 
 def save_snapshot(path: str, desc: abi.NsbModelDesc, params_u16: np.ndarray, density_grid: np.ndarray, aabb_scale: int, training_step: int = 0,
-                  loss: float = 0.0) -> None:
+                  loss: float = 0.0, compress: bool = True) -> None:
     import msgpack
 
     cfg = json.loads(json.dumps(_BASE_CONFIG))
@@ -41,8 +42,14 @@ def save_snapshot(path: str, desc: abi.NsbModelDesc, params_u16: np.ndarray, den
         "nerf": {"rgb": {"rays_per_batch": 1 << 12, "measured_batch_size": 0, "measured_batch_size_before_compaction": 0},
                  "dataset": {"aabb_scale": int(aabb_scale), "scale": 0.33, "offset": [0.5, 0.5, 0.5]}},
     }
+    blob = msgpack.packb(cfg, use_bin_type=True)
+    if path.lower().endswith(".ingp"):  # zstr::ostream: deflate with a gzip header (windowBits 15 + 16)
+        import zlib
+
+        co = zlib.compressobj(zlib.Z_DEFAULT_COMPRESSION if compress else zlib.Z_NO_COMPRESSION, zlib.DEFLATED, 15 + 16)
+        blob = co.compress(blob) + co.flush()
     with open(path, "wb") as fh:
-        fh.write(msgpack.packb(cfg, use_bin_type=True))
+        fh.write(blob)
 
 
 def load_snapshot(path: str):
@@ -50,7 +57,12 @@ def load_snapshot(path: str):
     import msgpack
 
     with open(path, "rb") as fh:
-        cfg = msgpack.unpackb(fh.read(), raw=False)
+        blob = fh.read()
+    if blob[:2] == b"\x1f\x8b" or (len(blob) > 1 and blob[0] == 0x78 and (blob[0] * 256 + blob[1]) % 31 == 0):  # zstr::istream: gzip or zlib, else plain
+        import zlib
+
+        blob = zlib.decompress(blob, 15 + 32)
+    cfg = msgpack.unpackb(blob, raw=False)
     enc, net, rgb = cfg["encoding"], cfg["network"], cfg["rgb_network"]
     snap = cfg["snapshot"]
     if snap.get("params_type", "__half") != "__half":

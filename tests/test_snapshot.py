@@ -44,6 +44,28 @@ def test_snapshot_roundtrip(tmp_path, scene):
         assert getattr(desc, f) == getattr(model.desc, f)
 
 
+def test_ingp_is_the_same_stream_behind_zlib(tmp_path, scene):
+    """.ingp = the msgpack stream through zstr (gzip-wrapped deflate, testbed.cu:168-171,3173-3176); uncompressed .ingp also loads."""
+    import gzip
+    import os
+
+    model, occ = scene
+    grid = _grid_from_occupancy(occ)
+    plain, packed, stored = (str(tmp_path / n) for n in ("s.msgpack", "s.ingp", "stored.ingp"))
+    snapshot.save_snapshot(plain, model.desc, model.params, grid, model.aabb_scale)
+    snapshot.save_snapshot(packed, model.desc, model.params, grid, model.aabb_scale)
+    snapshot.save_snapshot(stored, model.desc, model.params, grid, model.aabb_scale, compress=False)
+    assert gzip.open(packed, "rb").read() == open(plain, "rb").read() == gzip.open(stored, "rb").read()
+    assert os.path.getsize(packed) < os.path.getsize(plain) <= os.path.getsize(stored)
+    for path in (packed, stored):
+        desc, params, grid2, aabb_scale = snapshot.load_snapshot(path)
+        assert aabb_scale == 4 and np.array_equal(params, model.params) and np.array_equal(grid2, grid)
+    # a file named .ingp that holds the plain stream (zstr reads it through unchanged)
+    raw_ingp = str(tmp_path / "raw.ingp")
+    open(raw_ingp, "wb").write(open(plain, "rb").read())
+    assert np.array_equal(snapshot.load_snapshot(raw_ingp)[1], model.params)
+
+
 @pytest.mark.gpu
 def test_snapshot_to_render(tmp_path, scene, renderer):
     """load_snapshot path end to end: msgpack -> upload_model + upload_density_grid -> the same frame as the direct uploads."""
