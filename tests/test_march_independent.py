@@ -91,7 +91,7 @@ def box_tmin(mn, mx, o, d):
     return max(tmin, tzmin)
 
 
-def march(frame, bits, px, py, max_samples):
+def march(frame, bits, px, py, max_samples, want_ray=False):
     W, H = frame.width, frame.height
     cam = np.array(frame.camera1[:], np.float32)  # rolling shutter 0 -> camera1 exactly
     mn, mx = np.array(frame.render_aabb_min[:], np.float32), np.array(frame.render_aabb_max[:], np.float32)
@@ -105,7 +105,7 @@ def march(frame, bits, px, py, max_samples):
     t = max(box_tmin(mn, mx, o, d), F(0.05)) + F(1e-6)
     pos = [fma(d[k], t, o[k]) for k in range(3)]
     if not all(mn[k] <= pos[k] <= mx[k] for k in range(3)):
-        return []
+        return ([], o, d) if want_ray else []
     idir = [F(1.0) / v for v in d]
     pix = px + W * py
     t = fma(ld_random_val(frame.spp_index, (pix * 786433) & M32), calc_dt(t, cone), t)   # first-step jitter
@@ -134,7 +134,7 @@ def march(frame, bits, px, py, max_samples):
             t = t + calc_dt(t, cone)
             if not (t < t_target):
                 break
-    return out
+    return (out, o, d) if want_ray else out
 
 
 def test_python_march_equals_the_oracle_bit_for_bit(scene, oracle):
@@ -155,3 +155,68 @@ def test_python_march_equals_the_oracle_bit_for_bit(scene, oracle):
                 assert (mine[k][5], mine[k][6]) == (int(idx[i, k, 0]), int(idx[i, k, 1]))
             total += n
     assert total > 500
+
+
+def test_python_composite_equals_the_oracle_frame(scene, oracle):
+    """The rest of the frame from the formulas (composite_kernel_nerf :750-955, compact :2503, shade :2464-2482): Python march above ->
+    network outputs from the oracle's inference (cross-checked against numpy separately) -> float32 composite in Python, against
+    oracle.render pixel by pixel. exp/pow come from numpy instead of libm: agreement to a few float32 ulps, not bits."""
+    from nerfshop_b200 import abi
+
+    model, occ = scene
+    bits = np.unpackbits(occ, bitorder="little")
+    W, H = 14, 8
+    frame = syn.make_frame(model, syn.fox_camera0(), W, H)
+    fb_o, depth_o, st_o, margin = oracle.render(frame, want_margin=True)
+    tmin, tmax = np.array(frame.train_aabb_min[:], np.float32), np.array(frame.train_aabb_max[:], np.float32)
+    diag = tmax - tmin
+    cam = np.array(frame.camera1[:], np.float32)
+    fwd, org = cam[6:9], cam[9:12]
+    dt_range = MIN_STEP * F(16.0) - MIN_STEP
+    sat = F(1.0) - F(frame.min_transmittance)
+    n_samples = n_checked = 0
+    for py in range(H):
+        for px in range(W):
+            samples, o, d = march(frame, bits, px, py, 4000, want_ray=True)
+            c = np.zeros(4, np.float32)
+            depth, max_w, done_sat = F(0.0), F(0.0), False
+            if samples:
+                coords = np.zeros((len(samples), 7), np.float32)
+                for i, smp in enumerate(samples):
+                    coords[i, :3] = [(smp[2 + k] - tmin[k]) / diag[k] for k in range(3)]
+                    coords[i, 3] = (smp[1] - MIN_STEP) / dt_range
+                    coords[i, 4:] = [(d[k] + F(1.0)) * F(0.5) for k in range(3)]
+                raw = oracle.inference(coords).view(np.float16).astype(np.float32)  # [16, n]: rows 0-2 rgb, row 3 density
+                for i in range(len(samples)):
+                    n_samples += 1
+                    cpos = [fma(coords[i, k], diag[k], tmin[k]) for k in range(3)]
+                    T = F(1.0) - c[3]
+                    dtu = fma(coords[i, 3], dt_range, MIN_STEP)
+                    sigma = np.exp(raw[3, i])
+                    alpha = F(1.0) - np.exp(-sigma * dtu)
+                    w = alpha * T
+                    for k in range(3):
+                        c[k] = fma(F(1.0) / (F(1.0) + np.exp(-raw[k, i])), w, c[k])
+                    c[3] = c[3] + w
+                    if w > max_w:
+                        max_w = w
+                        q = [cpos[k] - org[k] for k in range(3)]
+                        depth = fma(fwd[2], q[2], fma(fwd[1], q[1], fwd[0] * q[0]))
+                    if c[3] > sat:
+                        c = c / c[3]
+                        done_sat = True
+                        break
+            pix_ambiguous = margin[py, px] <= 2e-5
+            expect = np.zeros(4, np.float32)
+            expect_depth = F(1e10)
+            if c[3] > F(0.001):
+                lin = [v / F(12.92) if v <= F(0.04045) else np.power((v + F(0.055)) / F(1.055), F(2.4)) for v in c[:3]]
+                expect = np.array(lin + [c[3]], np.float32)
+                if c[3] > F(0.2):
+                    expect_depth = depth
+            if not pix_ambiguous:
+                assert np.allclose(expect, fb_o[py, px], atol=3e-6, rtol=1e-5), (px, py, expect, fb_o[py, px])
+                assert np.isclose(expect_depth, depth_o[py, px], rtol=1e-5), (px, py, expect_depth, depth_o[py, px])
+                n_checked += 1
+    assert n_checked >= W * H - 2 and n_samples > 1000
+    assert n_samples == st_o.n_samples  # same termination decisions on every ray
