@@ -99,3 +99,45 @@ def test_oracle_grid_update_moves_occupancy_with_the_cage(scene):
     bmin = np.minimum(op.vertices.min(0), op.original_vertices.min(0)) - 1e-4
     bmax = np.maximum(op.vertices.max(0), op.original_vertices.max(0)) + 1e-4
     assert (hi >= bmin).all() and (lo <= bmax).all()
+
+
+def test_python_sample_draw_equals_the_oracle(scene, oracle):
+    """generate_grid_samples_nerf_nonuniform (common_nerf.cu:179-208) restated in Python on top of the host pcg32 mirror: the warped
+    position of every checked sample equals the oracle's, bit for bit — for both launches (the second one runs on m_rng advanced by 2^32)."""
+    import struct
+
+    G = 128 ** 3
+    rng0 = Pcg32(4242)
+    grid0 = np.zeros(abi.NSB_GRID_CELLS, np.float32)
+    grid0[::3] = 0.02      # some cells above the non-uniform threshold 0.01
+    grid0[5::7] = -1.0     # some untrained cells, which both passes must step over
+    n_uni, n_non, step = 5000, 3000, 7
+    u = grid_params(n_uni, n_non, rng0, ema_step=step, reset=False, n_cascades=3, apply_ops=False)
+    _, _, _, samples = oracle.update_density_grid(u, grid0, want_samples=True)
+
+    def next_float(r):
+        return np.float32(struct.unpack("<f", struct.pack("<I", (r.next_uint() >> 9) | 0x3F800000))[0]) - np.float32(1.0)
+
+    def inv_morton(m):
+        return [sum(((m >> (3 * b + k)) & 1) << b for b in range(7)) for k in range(3)]
+
+    f = np.float32
+    for i in list(range(0, n_uni, 97)) + list(range(n_uni, n_uni + n_non, 61)):
+        second = i >= n_uni
+        li, n_el, thresh = (i - n_uni, n_non, 0.01) if second else (i, n_uni, -0.01)
+        r = rng0.copy()
+        if second:
+            r.advance(1 << 32)
+        r.advance((li * 4) & 0xFFFFFFFF)
+        level = int(next_float(r) * f(3)) % 3
+        idx = 0
+        for j in range(10):
+            idx = (((li + step * n_el) * 56924617 + j * 19349663 + 96925573) & 0xFFFFFFFF) % G + level * G
+            if grid0[idx] > thresh:
+                break
+        x, y, z = inv_morton(idx % G)
+        rnd = [next_float(r) for _ in range(3)]
+        sc = f(2.0 ** level)
+        pos = [((f(c) + q) / f(128) - f(0.5)) * sc + f(0.5) for c, q in zip((x, y, z), rnd)]
+        pw = np.array([(pos[k] - f(-1.5)) / (f(2.5) - f(-1.5)) for k in range(3)], np.float32)
+        assert np.array_equal(pw.view(np.uint32), samples[i, :3].view(np.uint32)), (i, pw, samples[i, :3])
