@@ -13,7 +13,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libnerfshop_b200.so")
 SOURCES = ["nsb_kernels.cu", "nsb_host_geometry.cpp"]
-HEADERS = ["nsb_device.cuh", "nsb_tc.cuh", os.path.join("..", "..", "include", "nerfshop_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))) + [
+    os.path.join("..", "..", "include", "nerfshop_b200.h"), os.path.join("..", "host", "nerfshop_host.hpp")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-shared",

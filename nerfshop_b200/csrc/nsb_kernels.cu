@@ -197,9 +197,16 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	uint32_t pix = 0, n_steps = 0;
 	uint32_t c_hit = 0, c_samples = 0, c_old = 0;
 	uint32_t phase = 0;
-	// phase profile (thread 0 of each CTA; a handful of clock reads per round)
-	long long cyc_acq = 0, cyc_enc = 0, cyc_mlp = 0, cyc_comp = 0, n_rounds = 0;
+	// phase profile (thread 0 of each CTA; a handful of clock reads per round): diagnostic builds only (-DNSB_PROFILE), the
+	// product build keeps the registers and issue slots (nsb_debug_counters then reports rounds and CTAs only)
+#ifdef NSB_PROFILE
+#define NSB_CLOCK() clock64()
+	long long cyc_acq = 0, cyc_enc = 0, cyc_mlp = 0, cyc_comp = 0;
 	const long long cyc_start = clock64();
+#else
+#define NSB_CLOCK() 0ll
+#endif
+	uint32_t n_rounds = 0;
 
 	// shade_kernel_nerf (:2464-2482) for the ray this thread just finished (compact_kernel_nerf :2503 filter)
 	auto finish = [&](bool left_aabb, float cr, float cg, float cb, float ca, float ray_depth) {
@@ -221,7 +228,9 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 
 	for (;;) {
 		if (!tc::tile_any(C, alive || !exhausted)) break;
+#ifdef NSB_PROFILE
 		const long long c0 = clock64();
+#endif
 
 		// ---- acquire one occupied sample for this thread (refill the ray slot when it is free) ----
 		bool has_sample = false;
@@ -322,22 +331,30 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 		uint32_t dens[8], rgbo[8];
 		int first_pass = 1;
 		if (ops_on && any_poisson && f.poisson_target) first_pass = tc::tile_any(C, need_old) ? 0 : 1;
+#ifdef NSB_PROFILE
 		const long long c1 = clock64();
 		long long enc_cycles = 0;
+#endif
 #pragma unroll 1
 		for (int pass = first_pass; pass < 2; ++pass) {
 			const bool old_pass = pass == 0;
+#ifdef NSB_PROFILE
 			const long long e0 = clock64();
+#endif
 			encode_to_a32(TB.a32, m, old_pass ? need_old : has_sample, old_pass ? pw_old : pw, tid);
+#ifdef NSB_PROFILE
 			enc_cycles += clock64() - e0;
+#endif
 			tc::run_network(C, phase, dw, old_pass, dens, rgbo);
 			if (old_pass) {
 				sigma_old_raw = h_lo(dens[0]);
 				if (need_old) ++c_old;
 			}
 		}
+#ifdef NSB_PROFILE
 		const long long c2 = c1 + enc_cycles;
 		const long long c3 = clock64();
+#endif
 
 		// ---- composite_kernel_nerf :750-955 for this one sample ----
 		if (has_sample) {
@@ -403,7 +420,10 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 				TB.ray[R_DEPTH][tid] = ray_depth; TB.ray[R_MAXW][tid] = max_weight;
 			}
 		}
-		cyc_acq += c1 - c0; cyc_enc += c2 - c1; cyc_mlp += c3 - c2; cyc_comp += clock64() - c3; ++n_rounds;
+#ifdef NSB_PROFILE
+		cyc_acq += c1 - c0; cyc_enc += c2 - c1; cyc_mlp += c3 - c2; cyc_comp += clock64() - c3;
+#endif
+		++n_rounds;
 	}
 
 	tc::tc_fence_before();
@@ -411,11 +431,13 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, RENDER_TMEM_COLS);
 	if (tid == 0) {
 		atomicAdd(stats + ST_ROUNDS, (unsigned long long)n_rounds);
+#ifdef NSB_PROFILE
 		atomicAdd(stats + ST_CYC_ACQUIRE, (unsigned long long)cyc_acq);
 		atomicAdd(stats + ST_CYC_ENCODE, (unsigned long long)cyc_enc);
 		atomicAdd(stats + ST_CYC_MLP, (unsigned long long)cyc_mlp);
 		atomicAdd(stats + ST_CYC_COMPOSITE, (unsigned long long)cyc_comp);
 		atomicAdd(stats + ST_CYC_TOTAL, (unsigned long long)(clock64() - cyc_start));
+#endif
 		atomicAdd(stats + ST_CTAS, 1ull);
 	}
 
