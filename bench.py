@@ -13,8 +13,14 @@ e2e.value  : the same through the host-buffer entry point nsb_render_host: frame
              RGBA+depth framebuffer device->pinned host inside the timed region
 roofline   : the one kernel of the step (k_render_fused): algorithmic 512 B hash-grid gather per sample
               x samples of the frame / its CUDA-event duration, against measured HBM peak
-cpu_baseline / --impl reference: the CPU oracle (port of the reference path; the reference itself cannot be
-             built here) on all host cores on a bounded sample (a 1/64-resolution frame of the same orbit).
+gpu_baseline: (N = 1) the reference's OWN CUDA path — Testbed::render_nerf, NerfTracer::trace and every kernel they launch, compiled
+             by nvcc for sm_100a from /root/reference (oracle/_ref, built where the reference exists; only tiny-cuda-nn's network, an
+             absent submodule, is replaced by this repository's nsb_inference) — timed in the same process on the same cameras.
+configs    : (N = 1) BASELINE.json configs[2] (one cage, 3,072 tets) and configs[3] (unit-cube scene, 3 cages + membrane, poisson target)
+             at 1920x1080: native and reference-CUDA Mrays/s, samples, roofline fraction, L-inf between the two.
+cpu_baseline / --impl reference: the reference's Testbed::render_nerf compiled for the CPU (oracle/_ref/libnerfshop_ref.so: its own host
+             loop and kernels, OpenMP over the kernels' grids; the network is the oracle's CPU restatement) when that library is present,
+             else the oracle port; all host cores, bounded sample (a 1/64-resolution frame of the same orbit), median over the steps.
 """
 from __future__ import annotations
 
@@ -114,7 +120,9 @@ class ClockSampler:
 
 
 def cpu_reference_run(steps: int, warmup: int, threads: int | None = None):
-    """The CPU arm: oracle port of the reference path, all host cores, bounded sample per step."""
+    """The CPU arm: the reference's own render_nerf compiled for the CPU (oracle/_ref) when available, else the oracle port.
+    All host cores, threads pinned (OMP_PROC_BIND / OMP_PLACES are set by main() before any OpenMP runtime starts), bounded sample per step.
+    Returns (Mrays/s from the MEDIAN step, median ms, cores, samples per frame, kind, (p10, p90) ms)."""
     from nerfshop_b200 import synthetic as syn
     from oracle import oracle as orc
 
@@ -122,19 +130,125 @@ def cpu_reference_run(steps: int, warmup: int, threads: int | None = None):
     occ = syn.make_occupancy(model)
     o = orc.Oracle(model.desc, model.params, occ)
     cores = orc.set_threads(threads or (os.cpu_count() or 1))
+    kind = "port"
+    ref = None
+    try:
+        from oracle import ref as _ref
+
+        if _ref.available():
+            ref, kind = _ref, "reference"
+    except Exception:
+        ref = None
     cams = syn.orbit_cameras(N_ORBIT)
     times, samples = [], 0
     for i in range(warmup + steps):
         f = syn.make_frame(model, cams[(i * 7) % N_ORBIT], CPU_W, CPU_H)
         t0 = time.perf_counter()
-        _, _, st, _ = o.render(f)
+        if ref is not None:
+            _, _, info = ref.render(f, occ, o.inference)
+            n = info["n_inferred"] // 2  # the reference infers every (padded) batch twice
+        else:
+            _, _, st, _ = o.render(f)
+            n = st.n_samples
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-            samples += st.n_samples
-    total = sum(times)
-    mrays = CPU_W * CPU_H * len(times) / total / 1e6
-    return mrays, total / len(times) * 1e3, cores, samples / max(len(times), 1)
+            samples += n
+    med = float(np.median(times))
+    mrays = CPU_W * CPU_H / med / 1e6
+    return mrays, med * 1e3, cores, samples / max(len(times), 1), kind, (float(np.percentile(times, 10)) * 1e3, float(np.percentile(times, 90)) * 1e3)
+
+
+def measure_reference_cuda_and_edit_configs(r, model, occ, cams, fb, depth, flush, steps, dev):
+    """N = 1 only. (1) gpu_baseline: the reference's CUDA path (oracle/_ref, nvcc build of /root/reference's render path; network = nsb_inference)
+    on the orbit cameras of configs[1]. (2) configs[2] / configs[3] at 1080p, native and reference-CUDA. CUDA events around each frame, L2 flushed
+    between frames, 3 warm-up frames."""
+    import torch
+
+    from nerfshop_b200 import editing, synthetic as syn
+    from nerfshop_b200.renderer import NerfRenderer
+
+    try:
+        from oracle import ref
+
+        ref.cuda_lib()
+    except Exception as e:  # the library is built where /root/reference exists and travels with the repo
+        return {"unavailable": f"oracle/_ref/libnerfshop_ref_cuda.so not loadable: {e}"}, None
+
+    def time_frames(render_fn, frames, n):
+        ms = []
+        for i in range(3 + n):
+            flush.zero_()
+            fb.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            render_fn(frames[i % len(frames)])
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if i >= 3:
+                ms.append(e0.elapsed_time(e1))
+        return float(np.mean(ms)), ms
+
+    def both_arms(rr, rc, frames, n):
+        nat_ms, _ = time_frames(lambda f: rr.render(f, fb, depth), frames, n)
+        smp, kms = [], []
+        for f in frames:  # samples + fused-kernel time per camera (own events inside nsb_render)
+            rr.render(f, fb, depth)
+            st = rr.stats()
+            smp.append(st.n_samples)
+            kms.append(st.fused_ms)
+        ref_ms, _ = time_frames(lambda f: rc.render(f, rr, fb, depth), frames, n)
+        a = torch.zeros_like(fb)
+        b = torch.zeros_like(fb)
+        rr.render(frames[0], a, depth)
+        _, _, info = rc.render(frames[0], rr, b, depth)
+        torch.cuda.synchronize(dev)
+        hbm, _, _ = load_peaks()
+        s_mean, k_mean = float(np.mean(smp)), float(np.mean(kms))
+        return {
+            "native": {"value": W * H / nat_ms / 1e3, "unit": "Mrays/s", "ms_per_step": nat_ms, "samples_per_frame": s_mean, "kernel_ms": k_mean,
+                       "roofline_frac": s_mean * BYTES_PER_SAMPLE / (k_mean * 1e-3) / 1e9 / hbm},
+            "reference_cuda": {"value": W * H / ref_ms / 1e3, "unit": "Mrays/s", "ms_per_step": ref_ms, "inference_rows_frame0": info["n_inferred"], "inference_calls_frame0": info["n_calls"],
+                               "rounds_frame0": info["n_calls"] // 2},
+            "native_over_reference_cuda": ref_ms / nat_ms, "linf_rgba_native_vs_reference_cuda_frame0": float((a - b).abs().max().item()), "steps": n,
+        }
+
+    what = ("the reference's own CUDA render path (Testbed::render_nerf, NerfTracer::trace, compact/generate/composite/shade kernels; >= 12 launches + 3 host syncs per round, "
+            "every batch inferred twice) compiled by nvcc for sm_100a from /root/reference; tiny-cuda-nn's network (absent submodule) replaced by this repository's nsb_inference kernel")
+    frames = [syn.make_frame(model, cams[(i * 7) % N_ORBIT], W, H) for i in range(steps)]
+    rc = ref.RefCuda(occ)
+    res = both_arms(r, rc, frames, steps)
+    rc.close()
+    gpu_baseline = dict(res["reference_cuda"], kind="reference kernels + host loop, nvcc sm_100a", what=what, native_ms_same_cameras=res["native"]["ms_per_step"],
+                        linf_rgba_native_vs_reference_cuda_frame0=res["linf_rgba_native_vs_reference_cuda_frame0"], steps=steps, warmup=3)
+
+    extra = {}
+    # configs[2]: nerf/fox scale, ONE cage-deform operator (box cage, 8^3 lattice = 3,072 tets, MVC, +x face pulled), local rotations on
+    cage = editing.lattice_cage(model, (0.5, 0.62, 0.78), (0.17, 0.17, 0.17), n_lattice=8)
+    ops = [cage.to_op()]
+    r.set_edit_operators(ops)
+    rc = ref.RefCuda(occ, ops)
+    fr = [syn.make_frame(model, cams[(i * 7) % N_ORBIT], W, H, apply_operators=True) for i in range(4)]
+    extra["configs[2]"] = dict(both_arms(r, rc, fr, 6), workload=f"nerf/fox scale, one cage ({cage.tets.shape[0]} tets, {cage.lut_idx.size} CSR entries), 1080p, 4 orbit cameras")
+    rc.close()
+    r.set_edit_operators([])
+    # configs[3]: unit-cube scene (aabb_scale 1, cone angle 0: the reference's synthetic-Lego shape), 3 concurrent cages (6^3 lattices), membrane on the first, poisson target on
+    m1 = syn.make_model(seed=7, aabb_scale=1)
+    occ1 = syn.make_occupancy(m1)
+    r1 = NerfRenderer(r.device)
+    r1.upload_model(m1.desc, m1.params)
+    r1.upload_occupancy(occ1)
+    cages = [editing.lattice_cage(m1, (0.5, 0.62, 0.78), (0.17, 0.17, 0.17), n_lattice=6, membrane_seed=5),
+             editing.lattice_cage(m1, (0.5, 0.55, 0.27), (0.12, 0.12, 0.15), pull=(0.0, 0.08, 0.0), n_lattice=6),
+             editing.lattice_cage(m1, (0.41, 0.30, 0.42), (0.08, 0.14, 0.08), pull=(0.05, 0.0, 0.05), n_lattice=6, copy=True)]
+    ops = [c.to_op() for c in cages]
+    r1.set_edit_operators(ops)
+    rc = ref.RefCuda(occ1, ops)
+    fr = [syn.make_frame(m1, cams[(i * 7) % N_ORBIT], W, H, apply_operators=True, poisson_target=True) for i in range(4)]
+    extra["configs[3]"] = dict(both_arms(r1, rc, fr, 6), workload=f"unit-cube scene (aabb_scale 1, constant step), 3 cages ({sum(c.tets.shape[0] for c in cages)} tets) + membrane + poisson target, 1080p, 4 orbit cameras")
+    rc.close()
+    r1.close()
+    return gpu_baseline, extra
 
 
 def main():
@@ -144,24 +258,31 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-CUDA arm and the edit configurations (N = 1 extras)")
     args = ap.parse_args()
+    # pin the CPU arm's OpenMP threads (the round-1 arm swung 3.4x between two boxes with free-floating threads)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "nerf/fox 1080p free-viewpoint orbit, hash L=16 F=2 T=2^19, MLP 64x1 + 64x2 (configs[1])", "resolution": [W, H],
-              "cameras": f"{N_ORBIT}-view orbit, one camera per step", "parallelism": f"image-tile partition x{world}" if world > 1 else "single GPU"}
+              "cameras": f"{N_ORBIT}-view orbit about (0.5, 0.5, 0.5), radius 1.45, height +0.35 (NGP units; closer than BASELINE.md's radius 2.0: more covered pixels, more samples per frame), look-at centre, focal 1080 px, one camera per step (index 7*step mod {N_ORBIT})", "parallelism": f"image-tile partition x{world}" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         steps = max(1, min(args.steps, 8))
-        mrays, ms, cores, spf = cpu_reference_run(steps, min(args.warmup, 1))
-        sample = f"{CPU_W}x{CPU_H} frame (1/64 of the 1080p pixels) of the same orbit per step, {cores} threads"
+        warm = max(3, min(args.warmup, 3))
+        mrays, ms, cores, spf, kind, (p10, p90) = cpu_reference_run(steps, warm)
+        sample = f"{CPU_W}x{CPU_H} frame (1/64 of the 1080p pixels) of the same orbit per step, {cores} pinned threads, median of {steps} steps (p10 {p10:.0f} ms, p90 {p90:.0f} ms), {warm} warm-up"
+        note = ("the reference's Testbed::render_nerf / NerfTracer::trace / kernels compiled for the CPU from /root/reference (oracle/_ref); tiny-cuda-nn's network (absent submodule) = the oracle's CPU restatement"
+                if kind == "reference" else "CPU oracle port of the reference path (oracle/_ref/libnerfshop_ref.so not present)")
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": 0, "steps": steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16/f32", "data": "synthetic",
-            "config": dict(config, note="CPU oracle port of the reference path; the reference cannot be built here (tiny-cuda-nn/Eigen submodules absent)"),
-            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": 0, "steps": steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16/f32", "data": "synthetic",
+            "config": dict(config, note=note),
+            "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -273,6 +394,11 @@ def main():
 
     e2e_s = timed_wall(e2e_step, max(3, args.warmup // 2), args.steps)
 
+    # ---- N = 1 extras: the reference's own CUDA path on the same cameras, and the edit configurations ----
+    gpu_baseline, extra_configs = None, None
+    if world == 1 and not args.no_gpu_baseline:
+        gpu_baseline, extra_configs = measure_reference_cuda_and_edit_configs(r, model, occ, cams, fb, depth, flush, min(args.steps, 8), dev)
+
     if rank == 0:
         hbm_gbs, tflops, peak_kind = load_peaks()
         traffic = load_traffic()
@@ -296,10 +422,15 @@ def main():
                          "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None, "peak_source": peak_kind, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if world == 1 else None, "samples_per_launch": s_mean,
                          "tensor_tflops": s_mean * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12, "tensor_frac": s_mean * FLOP_PER_SAMPLE / (k_ms * 1e-3) / 1e12 / tflops},
         }
+        if world == 1:
+            out["gpu_baseline"] = gpu_baseline
+            if gpu_baseline and gpu_baseline.get("value"):
+                out["vs_gpu_baseline"] = {"device": value / gpu_baseline["value"], "north_star_target": 1.5}
+            out["configs"] = extra_configs
         if world == 1 and not args.no_cpu_baseline:
-            mrays, ms, cores, _ = cpu_reference_run(2, 0)
-            out["cpu_baseline"] = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                   "sample": f"2 frames of {CPU_W}x{CPU_H} (1/64 of the 1080p pixels) of the same orbit, {cores} threads"}
+            mrays, ms, cores, _, kind, (p10, p90) = cpu_reference_run(3, 1)
+            out["cpu_baseline"] = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                                   "sample": f"median of 3 frames of {CPU_W}x{CPU_H} (1/64 of the 1080p pixels) of the same orbit after 1 warm-up, {cores} pinned threads (p10 {p10:.0f} / p90 {p90:.0f} ms)"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

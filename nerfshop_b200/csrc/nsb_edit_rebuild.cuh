@@ -11,6 +11,7 @@
 // (plain, non-contracted fp32: every product and sum rounded separately, as gcc emits it for x86-64 without FMA), so the
 // device CSR is bit-identical to the host one; tests/test_gpu_edit_rebuild.py asserts exactly that.
 #pragma once
+#include "nsb_kabsch.h"
 
 namespace nsb {
 namespace rebuild {
@@ -127,43 +128,12 @@ __global__ void k_cage_bbox(const float* __restrict__ verts, uint32_t n, const f
 	}
 }
 
-// ---- TetMesh::update_local_rotations: orthogonal polar factor of the covariance by Newton iteration, in double -----------------
+// ---- TetMesh::update_local_rotations: proper Kabsch rotation per tet, in double (nsb_kabsch.h) ---------------------------------------
 __global__ void k_local_rotations(const float* __restrict__ verts, const float* __restrict__ orig, const uint32_t* __restrict__ tets, uint32_t n_tets,
                                   float* __restrict__ rots) {
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_tets) return;
-	double co[3] = {0, 0, 0}, cd[3] = {0, 0, 0};
-	uint32_t id[4];
-	for (int j = 0; j < 4; ++j) {
-		id[j] = tets[4 * t + j];
-		for (int k = 0; k < 3; ++k) { co[k] += orig[3 * id[j] + k]; cd[k] += verts[3 * id[j] + k]; }
-	}
-	for (int k = 0; k < 3; ++k) { co[k] /= 4.0; cd[k] /= 4.0; }
-	double Q[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-	for (int j = 0; j < 4; ++j)
-		for (int r = 0; r < 3; ++r)
-			for (int c = 0; c < 3; ++c) Q[r][c] += (orig[3 * id[j] + r] - co[r]) * (verts[3 * id[j] + c] - cd[c]);
-	bool ok = true;
-	for (int it = 0; it < 60 && ok; ++it) {
-		double det = Q[0][0] * (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) - Q[0][1] * (Q[1][0] * Q[2][2] - Q[1][2] * Q[2][0]) + Q[0][2] * (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]);
-		if (!(fabs(det) > 1e-300)) { ok = false; break; }
-		double inv[3][3];
-		inv[0][0] = (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) / det; inv[0][1] = (Q[0][2] * Q[2][1] - Q[0][1] * Q[2][2]) / det; inv[0][2] = (Q[0][1] * Q[1][2] - Q[0][2] * Q[1][1]) / det;
-		inv[1][0] = (Q[1][2] * Q[2][0] - Q[1][0] * Q[2][2]) / det; inv[1][1] = (Q[0][0] * Q[2][2] - Q[0][2] * Q[2][0]) / det; inv[1][2] = (Q[0][2] * Q[1][0] - Q[0][0] * Q[1][2]) / det;
-		inv[2][0] = (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]) / det; inv[2][1] = (Q[0][1] * Q[2][0] - Q[0][0] * Q[2][1]) / det; inv[2][2] = (Q[0][0] * Q[1][1] - Q[0][1] * Q[1][0]) / det;
-		double delta = 0.0, N[3][3];
-		for (int r = 0; r < 3; ++r)
-			for (int c = 0; c < 3; ++c) {
-				N[r][c] = 0.5 * (Q[r][c] + inv[c][r]);
-				delta = fmax(delta, fabs(N[r][c] - Q[r][c]));
-			}
-		for (int r = 0; r < 3; ++r)
-			for (int c = 0; c < 3; ++c) Q[r][c] = N[r][c];
-		if (delta < 1e-14) break;
-	}
-	float* R = rots + 9 * (size_t)t;  // column-major
-	for (int r = 0; r < 3; ++r)
-		for (int c = 0; c < 3; ++c) R[c * 3 + r] = ok ? (float)Q[r][c] : (r == c ? 1.0f : 0.0f);
+	tet_rotation(verts, orig, tets + 4 * (size_t)t, rots + 9 * (size_t)t);
 }
 
 // ---- TetMesh::build_tet_grid, pass 1: one CTA per (tet, cascade); its threads stride over the cells of the tet's box -----------

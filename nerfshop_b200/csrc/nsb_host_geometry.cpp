@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/nerfshop_b200.h"
+#include "nsb_kabsch.h"
 
 namespace {
 
@@ -247,43 +248,9 @@ extern "C" NsbStatus nsb_interpolate_with_mvc(const float* weights, uint32_t n_p
 	return NSB_OK;
 }
 
-// Kabsch rotation per tet: C = sum (orig_k - c_o)(def_k - c_d)^T, R = U V^T = the orthogonal polar factor of C
-// (no reflection fix, as in the reference). Computed by Newton iteration Q <- (Q + Q^-T)/2 in double.
+// Kabsch rotation per tet (always a proper rotation, like svd3.h's U V^T): nsb_kabsch.h
 extern "C" NsbStatus nsb_local_rotations(const float* vertices, const float* original_vertices, const uint32_t* tets, uint32_t n_tets, float* rotations) {
 	if (!vertices || !original_vertices || !tets || !rotations) return NSB_ERR_INVALID;
-	for (uint32_t t = 0; t < n_tets; ++t) {
-		double co[3] = {0, 0, 0}, cd[3] = {0, 0, 0};
-		for (int j = 0; j < 4; ++j)
-			for (int k = 0; k < 3; ++k) {
-				co[k] += original_vertices[3 * tets[4 * t + j] + k];
-				cd[k] += vertices[3 * tets[4 * t + j] + k];
-			}
-		for (int k = 0; k < 3; ++k) { co[k] /= 4.0; cd[k] /= 4.0; }
-		double Q[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-		for (int j = 0; j < 4; ++j)
-			for (int r = 0; r < 3; ++r)
-				for (int c = 0; c < 3; ++c)
-					Q[r][c] += (original_vertices[3 * tets[4 * t + j] + r] - co[r]) * (vertices[3 * tets[4 * t + j] + c] - cd[c]);
-		bool ok = true;
-		for (int it = 0; it < 60 && ok; ++it) {
-			double det = Q[0][0] * (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) - Q[0][1] * (Q[1][0] * Q[2][2] - Q[1][2] * Q[2][0]) + Q[0][2] * (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]);
-			if (!(std::fabs(det) > 1e-300)) { ok = false; break; }
-			double inv[3][3];  // inverse
-			inv[0][0] = (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) / det; inv[0][1] = (Q[0][2] * Q[2][1] - Q[0][1] * Q[2][2]) / det; inv[0][2] = (Q[0][1] * Q[1][2] - Q[0][2] * Q[1][1]) / det;
-			inv[1][0] = (Q[1][2] * Q[2][0] - Q[1][0] * Q[2][2]) / det; inv[1][1] = (Q[0][0] * Q[2][2] - Q[0][2] * Q[2][0]) / det; inv[1][2] = (Q[0][2] * Q[1][0] - Q[0][0] * Q[1][2]) / det;
-			inv[2][0] = (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]) / det; inv[2][1] = (Q[0][1] * Q[2][0] - Q[0][0] * Q[2][1]) / det; inv[2][2] = (Q[0][0] * Q[1][1] - Q[0][1] * Q[1][0]) / det;
-			double delta = 0.0, N[3][3];
-			for (int r = 0; r < 3; ++r)
-				for (int c = 0; c < 3; ++c) {
-					N[r][c] = 0.5 * (Q[r][c] + inv[c][r]);
-					delta = std::max(delta, std::fabs(N[r][c] - Q[r][c]));
-				}
-			std::memcpy(Q, N, sizeof(Q));
-			if (delta < 1e-14) break;
-		}
-		float* R = rotations + 9 * (size_t)t;  // column-major
-		for (int r = 0; r < 3; ++r)
-			for (int c = 0; c < 3; ++c) R[c * 3 + r] = ok ? (float)Q[r][c] : (r == c ? 1.0f : 0.0f);
-	}
+	for (uint32_t t = 0; t < n_tets; ++t) nsb::tet_rotation(vertices, original_vertices, tets + 4 * (size_t)t, rotations + 9 * (size_t)t);
 	return NSB_OK;
 }

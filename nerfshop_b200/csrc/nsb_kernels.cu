@@ -152,6 +152,9 @@ struct __align__(128) RenderSmem {
 };
 constexpr uint32_t RENDER_TMEM_COLS = NSB_TILES <= 1 ? 64 : NSB_TILES <= 2 ? 128 : NSB_TILES <= 4 ? 256 : 512;
 
+// OPS = false: the instantiation for frames without edit operators (f.apply_ops == 0 or no operator uploaded) carries none of the deform /
+// membrane code in its hot loop (the loop has to fit the instruction cache: profiles/README.md item 6).
+template <bool OPS>
 __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
                                                       float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	C.a32 = TB.a32; C.a64 = TB.a64; C.w_addr = tc::smem_u32(RS.w); C.mma_bar = &TB.mma_bar; C.tmem = tmem_base + tile * tc::TMEM_COLS; C.row = tid;
 	C.bar_id = 1 + tile;
 
-	const bool ops_on = f.apply_ops && n_ops > 0;
+	constexpr bool ops_on = OPS;  // the host picks the instantiation: f.apply_ops && n_ops > 0
 
 	// what stays in registers across a round
 	bool alive = false, exhausted = false;  // exhausted is warp-uniform: the queue had nothing left when this warp last asked
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 			float dtu = unwarp_dt(dtw);
 			float sigma = network_to_density(h_lo(dens[0]), f.density_act);  // row 3 = density MLP out[0] (extract_density)
 			float alpha;
-			const bool membrane = mem.dob > 1e-9f;
+			const bool membrane = OPS && mem.dob > 1e-9f;
 			if (empty) {
 				alpha = 0.0f;
 			} else if (membrane) {
@@ -925,9 +928,10 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	// k_render_fused: ONE CTA of NSB_TILES tiles per SM (512 threads x 128 registers = the whole register file; TMEM 64 columns
 	// per tile; shared memory 20 KB weights + 23 KB per tile).
 	c->ctas_per_sm = 1;
-	CU(set_smem((const void*)k_render_fused, sizeof(RenderSmem), 1));
+	CU(set_smem((const void*)k_render_fused<false>, sizeof(RenderSmem), 1));
+	CU(set_smem((const void*)k_render_fused<true>, sizeof(RenderSmem), 1));
 	cudaFuncAttributes fa;
-	CU(cudaFuncGetAttributes(&fa, k_render_fused));
+	CU(cudaFuncGetAttributes(&fa, k_render_fused<false>));
 	const int by_smem_tile = (int)(prop.sharedMemPerMultiprocessor / (sizeof(tc::TileSmem) + 1024));
 	{   // the operator-level kernels: one tile per CTA, residency from registers / shared memory
 		cudaFuncAttributes fi;
@@ -945,7 +949,10 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 		CU(set_smem((const void*)k_inference<true>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
 		CU(set_smem((const void*)k_density_grid_update, sizeof(tc::TileSmem), c->grid_update_ctas_per_sm));
 	}
-	if (const char* e = getenv("NSB_CARVEOUT")) CU(cudaFuncSetAttribute(k_render_fused, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));  // experiments
+	if (const char* e = getenv("NSB_CARVEOUT")) {  // experiments
+		CU(cudaFuncSetAttribute(k_render_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+		CU(cudaFuncSetAttribute(k_render_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+	}
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
 	if (const char* e = getenv("NSB_CHUNK")) { int v = atoi(e); if (v >= 0 && v <= 65535) c->refill_thr |= v << 8; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
@@ -1551,7 +1558,8 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		CU(cudaEventRecord(c->evm, stream));
 		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
 		if (grid > (my_tiles + NSB_TILES - 1) / NSB_TILES) grid = (uint32_t)((my_tiles + NSB_TILES - 1) / NSB_TILES);
-		k_render_fused<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
+		auto kernel = (f.apply_ops && c->n_ops > 0) ? k_render_fused<true> : k_render_fused<false>;
+		kernel<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
 		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
 		                                                          c->refill_thr, c->dda_budget);
 		CU(cudaGetLastError());

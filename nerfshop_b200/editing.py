@@ -229,3 +229,24 @@ class AffineDuplication:
         op.hide_original = int(self.hide_original)
         op.correct_dir = int(self.correct_dir)
         return op, {}
+
+
+def lattice_cage(model, center, half, pull=(0.10, 0.03, 0.0), n_lattice=3, copy=False, membrane_seed=None):
+    """A box cage around `center` (world units) with a lattice tet mesh inside it (5-6 tets per lattice cube; TetGen is not available),
+    its +x face pulled by `pull`; optionally seeded membrane (Poisson) arrays. Used by the test fixtures (E1 / E3 of SURVEY.md section 8d) and by
+    bench.py's edit configurations."""
+    center, half = np.asarray(center, np.float32), np.asarray(half, np.float32)
+    cv, ct = box_cage(center - half, center + half)
+    tv, tets = lattice_tets(center - 0.97 * half, center + 0.97 * half, n_lattice)
+    op = CageDeformation(model.aabb_min, model.aabb_max, cv, ct, tv, tets, copy=copy)
+    moved = op.cage_original.copy()
+    moved[moved[:, 0] > center[0]] += np.asarray(pull, np.float32)  # pull the +x face
+    op.cage_vertices = moved
+    op.update_tet_mesh()
+    if membrane_seed is not None:
+        rng = np.random.default_rng(membrane_seed)
+        nv = op.vertices.shape[0]
+        shs = rng.uniform(-0.3, 0.3, (nv, 27)).astype(np.float32)
+        shs[:, [0, 9, 18]] += 1.2  # DC terms: a visible base colour
+        op.set_membrane(shs, rng.uniform(0.0, 30.0, nv).astype(np.float32), rng.uniform(-2.0, 6.0, nv).astype(np.float32), amplitude=1.0, apply=True)
+    return op

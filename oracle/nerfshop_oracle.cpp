@@ -100,8 +100,10 @@ inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }
 inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
-// Eigen a.dot(b) for 3-vectors as nvcc compiles it: fma(z,z', fma(y,y', x*x'))
-inline float dot3(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+// Eigen a.dot(b) for 3-vectors: Eigen's unrolled reduction tree is x0*y0 + (x1*y1 + x2*y2) (Redux.h, redux_novec_unroller) and nvcc 12.9
+// contracts it to fma(x0,y0, fma(x1,y1, x2*y2)) — read off the PTX/SASS of the reference's own kernels (oracle/_ref, nvcc build) and
+// confirmed bit for bit on the GPU (tests/test_gpu_vs_ref_cuda.py). Round 1 had the opposite association.
+inline float dot3(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 // Eigen cross: (a.y*b.z - a.z*b.y, ...) ; nvcc contracts each as fma(a.y, b.z, -(a.z*b.y))
 inline V3 cross3(V3 a, V3 b) {
 	return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
@@ -486,16 +488,16 @@ inline void bary_tet(V3 a, V3 b, V3 c, V3 d, V3 p, float* out) {
 	out[0] = va6 * v6; out[1] = vb6 * v6; out[2] = vc6 * v6; out[3] = vd6 * v6;
 }
 inline V3 ldv(const float* p, uint32_t i) { return v3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
-inline V3 bary_mix(const float* b, V3 a0, V3 a1, V3 a2, V3 a3) { // b.x*a0 + b.y*a1 + b.z*a2 + b.w*a3, left to right
-	return v3(fmaf(b[3], a3.x, fmaf(b[2], a2.x, fmaf(b[1], a1.x, b[0] * a0.x))),
-	          fmaf(b[3], a3.y, fmaf(b[2], a2.y, fmaf(b[1], a1.y, b[0] * a0.y))),
-	          fmaf(b[3], a3.z, fmaf(b[2], a2.z, fmaf(b[1], a1.z, b[0] * a0.z))));
+inline V3 bary_mix(const float* b, V3 a0, V3 a1, V3 a2, V3 a3) { // ((b.x*a0 + b.y*a1) + b.z*a2) + b.w*a3; nvcc: fma(b3,a3, fma(b2,a2, fma(b0,a0, b1*a1)))
+	return v3(fmaf(b[3], a3.x, fmaf(b[2], a2.x, fmaf(b[0], a0.x, b[1] * a1.x))),
+	          fmaf(b[3], a3.y, fmaf(b[2], a2.y, fmaf(b[0], a0.y, b[1] * a1.y))),
+	          fmaf(b[3], a3.z, fmaf(b[2], a2.z, fmaf(b[0], a0.z, b[1] * a1.z))));
 }
 inline V3 matvec3(const float* M /*col-major*/, V3 v) {
-	return v3(fmaf(M[6], v.z, fmaf(M[3], v.y, M[0] * v.x)), fmaf(M[7], v.z, fmaf(M[4], v.y, M[1] * v.x)), fmaf(M[8], v.z, fmaf(M[5], v.y, M[2] * v.x)));
+	return v3(fmaf(M[0], v.x, fmaf(M[3], v.y, M[6] * v.z)), fmaf(M[1], v.x, fmaf(M[4], v.y, M[7] * v.z)), fmaf(M[2], v.x, fmaf(M[5], v.y, M[8] * v.z)));  // row . v, Eigen tree
 }
 inline V3 matTvec3(const float* M /*col-major*/, V3 v) {
-	return v3(fmaf(M[2], v.z, fmaf(M[1], v.y, M[0] * v.x)), fmaf(M[5], v.z, fmaf(M[4], v.y, M[3] * v.x)), fmaf(M[8], v.z, fmaf(M[7], v.y, M[6] * v.x)));
+	return v3(fmaf(M[0], v.x, fmaf(M[1], v.y, M[2] * v.z)), fmaf(M[3], v.x, fmaf(M[4], v.y, M[5] * v.z)), fmaf(M[6], v.x, fmaf(M[7], v.y, M[8] * v.z)));
 }
 
 // find the first tet of `cell`'s candidate list that contains p (cage_deformation.cu:228-248)
@@ -585,12 +587,12 @@ void poisson_one(const NsbEditOp* ops, int n_ops, V3 pos_w, float* sh27, float* 
 		const uint32_t* tv = op.tets + 4 * (size_t)t;
 		for (int k = 0; k < 27; ++k) {
 			sh27[k] = fmaf(b[3], op.boundary_shs[27 * (size_t)tv[3] + k], fmaf(b[2], op.boundary_shs[27 * (size_t)tv[2] + k],
-			          fmaf(b[1], op.boundary_shs[27 * (size_t)tv[1] + k], b[0] * op.boundary_shs[27 * (size_t)tv[0] + k])));
+			          fmaf(b[0], op.boundary_shs[27 * (size_t)tv[0] + k], b[1] * op.boundary_shs[27 * (size_t)tv[1] + k])));
 		}
 		float od = fmaf(b[3], op.boundary_outside_density[tv[3]], fmaf(b[2], op.boundary_outside_density[tv[2]],
-		           fmaf(b[1], op.boundary_outside_density[tv[1]], b[0] * op.boundary_outside_density[tv[0]])));
+		           fmaf(b[0], op.boundary_outside_density[tv[0]], b[1] * op.boundary_outside_density[tv[1]])));
 		float rd = fmaf(b[3], op.boundary_residual_density[tv[3]], fmaf(b[2], op.boundary_residual_density[tv[2]],
-		           fmaf(b[1], op.boundary_residual_density[tv[1]], b[0] * op.boundary_residual_density[tv[0]])));
+		           fmaf(b[0], op.boundary_residual_density[tv[0]], b[1] * op.boundary_residual_density[tv[1]])));
 		*out_density = op.residual_amplitude * od;
 		*residual_density = op.residual_amplitude * rd;
 	}
@@ -1119,7 +1121,7 @@ int orc_update_density_grid(const OrcScene* s, const NsbGridUpdate* u, float* gr
 				if (t < 0) continue;
 				const uint32_t* tv = op.tets + 4 * (size_t)t;
 				float res = fmaf(b[3], op.boundary_residual_density[tv[3]], fmaf(b[2], op.boundary_residual_density[tv[2]],
-				            fmaf(b[1], op.boundary_residual_density[tv[1]], b[0] * op.boundary_residual_density[tv[0]])));
+				            fmaf(b[0], op.boundary_residual_density[tv[0]], b[1] * op.boundary_residual_density[tv[1]])));
 				h = hadd(h, f2h(res));                                                          // half += half (:379)
 			}
 		}

@@ -47,7 +47,7 @@ def lib() -> C.CDLL:
         l.ref_map_rays.argtypes = [C.POINTER(abi.NsbEditOp), C.c_int, V, V, C.c_uint32]
         l.ref_poisson_residuals.argtypes = [C.POINTER(abi.NsbEditOp), C.c_int, V, C.c_uint32, V, V, V]
         l.ref_compute_mvc.argtypes = [V, C.c_uint32, V, C.c_uint32, V, C.c_uint32, V, C.c_float, C.c_int]
-        l.ref_tet_mesh_build.argtypes = [V, V, C.c_uint32, V, C.c_uint32, V, V, V, V, V, C.c_uint32, V, V]
+        l.ref_tet_mesh_build.argtypes = [V, V, C.c_uint32, V, C.c_uint32, V, V, V, V, V, C.c_uint32, V, V, V]
         l.ref_svd3.argtypes = [C.c_uint32, V, V]
         l.ref_set_parallel.argtypes = [C.c_int]
         _lib = l
@@ -231,9 +231,10 @@ def tet_mesh_build(original_vertices, deformed_vertices, tets, amin, amax, lut_c
     idx = np.zeros(lut_capacity, np.uint32)
     n_idx = C.c_uint32()
     bbox = np.zeros(12, np.float32)
-    rc = lib().ref_tet_mesh_build(_p(ov), _p(dv), ov.shape[0], _p(tt), n_t, _p(amin), _p(amax), _p(rot), _p(off), _p(idx), lut_capacity, C.byref(n_idx), _p(bbox))
+    obits = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8)
+    rc = lib().ref_tet_mesh_build(_p(ov), _p(dv), ov.shape[0], _p(tt), n_t, _p(amin), _p(amax), _p(rot), _p(off), _p(idx), lut_capacity, C.byref(n_idx), _p(bbox), _p(obits))
     assert rc == 0, rc
-    return rot, off, idx[: n_idx.value].copy(), bbox.reshape(4, 3)
+    return rot, off, idx[: n_idx.value].copy(), bbox.reshape(4, 3), obits
 
 
 def svd3_rotation(A):

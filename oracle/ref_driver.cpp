@@ -245,7 +245,7 @@ struct RefTetMesh {
 // update_local_rotations + build_tet_grid. Outputs are copied out of the mesh's (host-backed) GPUMemory members.
 int ref_tet_mesh_build(const float* original_vertices, const float* deformed_vertices, uint32_t n_v, const uint32_t* tets, uint32_t n_tets, const float* amin, const float* amax,
                        float* rotations /*9 per tet*/, uint32_t* lut_offsets /*NSB_GRID_CELLS+1*/, uint32_t* lut_idx, uint32_t lut_capacity, uint32_t* n_lut_idx,
-                       float* bbox /*12: bbox min,max, warped bbox min,max*/) {
+                       float* bbox /*12: bbox min,max, warped bbox min,max*/, uint8_t* original_bitfield /*NSB_BITFIELD_BYTES*/) {
 	std::vector<Eigen::Vector3f> ov(n_v);
 	for (uint32_t i = 0; i < n_v; ++i) ov[i] = Eigen::Vector3f(original_vertices[3 * i], original_vertices[3 * i + 1], original_vertices[3 * i + 2]);
 	std::vector<uint32_t> indices, tt(tets, tets + 4 * (size_t)n_tets);
@@ -260,6 +260,7 @@ int ref_tet_mesh_build(const float* original_vertices, const float* deformed_ver
 	*n_lut_idx = (uint32_t)mesh.tet_lut_idx.size();
 	if (mesh.tet_lut_idx.size() > lut_capacity) return 2;
 	memcpy(lut_idx, mesh.tet_lut_idx.data(), mesh.tet_lut_idx.size() * sizeof(uint32_t));
+	mesh.original_bitfield_gpu.copy_to_host(original_bitfield, NSB_BITFIELD_BYTES);
 	const Eigen::Vector3f v[4] = {mesh.bbox.min, mesh.bbox.max, mesh.warped_bbox.min, mesh.warped_bbox.max};
 	for (int k = 0; k < 4; ++k) { bbox[3 * k] = v[k].x(); bbox[3 * k + 1] = v[k].y(); bbox[3 * k + 2] = v[k].z(); }
 	return (int)mesh.tet_lut_offsets.size() == (int)NSB_GRID_CELLS + 1 ? 0 : 3;

@@ -16,8 +16,8 @@ def fma(a, b, c):
     return (np.asarray(a, F64) * np.asarray(b, F64) + np.asarray(c, F64)).astype(F32)
 
 
-def dot3(a, b):   # fma(z,z', fma(y,y', x*x'))
-    return fma(a[..., 2], b[..., 2], fma(a[..., 1], b[..., 1], (a[..., 0] * b[..., 0]).astype(F32)))
+def dot3(a, b):   # Eigen's reduction tree x0*y0 + (x1*y1 + x2*y2) as nvcc contracts it: fma(x,x', fma(y,y', z*z'))
+    return fma(a[..., 0], b[..., 0], fma(a[..., 1], b[..., 1], (a[..., 2] * b[..., 2]).astype(F32)))
 
 
 def cross3(a, b):  # fma(a.y, b.z, -(a.z*b.y)), ...
@@ -55,12 +55,12 @@ def map_one(op, pw, dw):
             v6 = F32(1.0 / F64(stp(vab, vac, vad)))
             bary = [stp(vbp, vbd, vbc) * v6, stp(vap, vac, vad) * v6, stp(vap, vad, vab) * v6, stp(vap, vab, vac) * v6]
             O = op.original_vertices[op.tets[t]]
-            canon = fma(bary[3], O[3], fma(bary[2], O[2], fma(bary[1], O[1], (bary[0] * O[0]).astype(F32))))
+            canon = fma(bary[3], O[3], fma(bary[2], O[2], fma(bary[0], O[0], (bary[1] * O[1]).astype(F32))))
             pw = ((canon - mn) / diag).astype(F32)
             if op.use_local_rotations:
                 R = op.rotations[t].reshape(3, 3).T   # column-major storage -> R[r][c]
                 ud = fma(dw, F32(2.0), F32(-1.0))
-                rd = np.array([fma(R[r, 2], ud[2], fma(R[r, 1], ud[1], R[r, 0] * ud[0])) for r in range(3)], F32)
+                rd = np.array([fma(R[r, 0], ud[0], fma(R[r, 1], ud[1], R[r, 2] * ud[2])) for r in range(3)], F32)
                 dw = ((rd + F32(1.0)) * F32(0.5)).astype(F32)
             in_def = True
     empty = False

@@ -98,8 +98,8 @@ def march(frame, bits, px, py, max_samples, want_ray=False):
     cone = F(frame.cone_angle_constant)
     uvx, uvy = (F(px) + F(0.5)) / F(W), (F(py) + F(0.5)) / F(H)   # spp 0: pixel centre
     dl = [(uvx - F(frame.screen_center[0])) * F(W) / F(frame.focal_length[0]), (uvy - F(frame.screen_center[1])) * F(H) / F(frame.focal_length[1]), F(1.0)]
-    d = [fma(cam[6 + r], dl[2], fma(cam[3 + r], dl[1], cam[r] * dl[0])) for r in range(3)]
-    n = np.sqrt(fma(d[2], d[2], fma(d[1], d[1], d[0] * d[0])))
+    d = [fma(cam[r], dl[0], fma(cam[3 + r], dl[1], cam[6 + r] * dl[2])) for r in range(3)]  # Eigen tree m0*d0 + (m1*d1 + m2*d2), nvcc's contraction
+    n = np.sqrt(fma(d[0], d[0], fma(d[1], d[1], d[2] * d[2])))
     d = [v / n for v in d]
     o = [cam[9], cam[10], cam[11]]
     t = max(box_tmin(mn, mx, o, d), F(0.05)) + F(1e-6)
@@ -201,7 +201,7 @@ def test_python_composite_equals_the_oracle_frame(scene, oracle):
                     if w > max_w:
                         max_w = w
                         q = [cpos[k] - org[k] for k in range(3)]
-                        depth = fma(fwd[2], q[2], fma(fwd[1], q[1], fwd[0] * q[0]))
+                        depth = fma(fwd[0], q[0], fma(fwd[1], q[1], fwd[2] * q[2]))
                     if c[3] > sat:
                         c = c / c[3]
                         done_sat = True

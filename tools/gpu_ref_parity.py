@@ -60,6 +60,41 @@ for ci in (17, 63):
         print(f"cam {ci} march {name} vs ref_cuda: {tot} samples, count mismatches {bad_c}, t mismatches {bad_t}, pos mismatches {bad_p} (max {maxulp} ulp)")
     print("  native vs oracle bit-equal:", np.array_equal(rec_n, rec_o), np.array_equal(cnt_n, cnt_o))
 
+# ---- edits: map_rays / poisson through E3 + affine ------------------------------------------------------------------
+from edit_fixtures import e3
+from nerfshop_b200 import editing
+a_ = 0.4
+ROT = np.array([[np.cos(a_), -np.sin(a_), 0], [np.sin(a_), np.cos(a_), 0], [0, 0, 1]], np.float32)
+ops = [c.to_op() for c in e3(model)]
+ops.append(editing.AffineDuplication((0.5, 0.5, 0.5), (0.12, 0.12, 0.12), (0.03, 0.0, -0.1), rotation=ROT, hide_original=True, correct_dir=True).to_op())
+r.set_edit_operators(ops)
+rce = ref.RefCuda(occ, ops)
+oe = orc.Oracle(model.desc, model.params, occ, ops)
+rng = np.random.default_rng(3)
+n = 400_000
+c = np.zeros((n, 7), np.float32)
+c[:, :3] = rng.uniform(0.38, 0.64, (n, 3))
+d = rng.standard_normal((n, 3)).astype(np.float32)
+c[:, 4:] = (d / np.linalg.norm(d, axis=1, keepdims=True) + 1) * 0.5
+cn, mn_ = r.map_rays(c)
+cr_, mr_ = rce.map_rays(c)
+co_, mo_ = oe.map_rays(c)
+print("map_rays native vs oracle bit-equal:", np.array_equal(cn, co_), np.array_equal(mn_, mo_))
+moved = (cr_[:, :3] != c[:, :3]).any(axis=1)
+print(f"map_rays native vs ref_cuda: moved {moved.sum()}, masked {mr_.sum()}; mask mismatches {(mn_ != mr_).sum()}; rows differing pos {(cn[:, :3] != cr_[:, :3]).any(axis=1).sum()} dir {(cn[:, 4:] != cr_[:, 4:]).any(axis=1).sum()}; max abs pos {np.abs(cn[:, :3] - cr_[:, :3]).max():.3e} dir {np.abs(cn[:, 4:] - cr_[:, 4:]).max():.3e}")
+shn, odn, rdn = r.poisson_residuals(c)
+shr, odr, rdr = rce.poisson_residuals(c)
+print(f"poisson native vs ref_cuda: inside {(odr != 0).sum()}; membership mismatches {((odn != 0) != (odr != 0)).sum()}; od differ {(odn != odr).sum()} max {np.abs(odn - odr).max():.3e}; sh differ {(shn != shr).any(axis=1).sum()} max {np.abs(shn - shr).max():.3e}")
+fe = syn.make_frame(model, cams[17], W, H)
+fe.apply_operators, fe.poisson_target = 1, 1
+fbn, _ = r.render(fe)
+fbr, _, _ = rce.render(fe, r)
+torch.cuda.synchronize()
+e = (fbn - fbr).abs().amax(-1)
+print("edited frame native vs ref_cuda L-inf %.3e, > 1e-4: %d, > 1e-3: %d" % (e.max().item(), (e > 1e-4).sum().item(), (e > 1e-3).sum().item()))
+r.set_edit_operators([])
+rce.close()
+
 # ---- frames -------------------------------------------------------------------------------------------------------------
 f = syn.make_frame(model, cams[17], W, H)
 fb_n, d_n = r.render(f)
