@@ -311,13 +311,13 @@ def main():
     n_tiles = [r.tiles_for_rank(W, H, k, world) for k in range(world)]
     max_tiles = max(n_tiles)
     if world > 1:
-        shard = torch.zeros((max_tiles * 128, 4), dtype=torch.float32, device=dev)
-        gathered = torch.zeros((world, max_tiles * 128, 4), dtype=torch.float32, device=dev)
+        shard = torch.zeros(max_tiles * 128 * 5, dtype=torch.float32, device=dev)            # [tiles*128 float4 | tiles*128 depth]
+        gathered = torch.zeros((world, max_tiles * 128 * 5), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     host_fb = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
     host_depth = torch.zeros((H, W), dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream(dev)
-    launches_per_step = 2 + (world if world > 1 else 0)  # k_prepare_rays + k_render_fused (+ k_pack_tiles and world-1 x unpack)
+    launches_per_step = 2 + (2 if world > 1 else 0)  # k_prepare_rays + k_render_fused (+ k_pack_tiles + k_unpack_gathered; the all-gather is NCCL's)
 
     def device_step(i):
         """One frame, output left in HBM (for N > 1: render own tiles, pack, all-gather, unpack every shard)."""
@@ -325,7 +325,7 @@ def main():
         fb.zero_()  # render_buffer.clear_frame
         r.render(f, fb, depth)
         if world > 1:
-            parallel.gather_framebuffer(r, fb, rank, world, shard, gathered)
+            parallel.gather_framebuffer(r, fb, rank, world, shard, gathered, depth)
 
     def timed(step_fn, n_warm, n_steps):
         for i in range(n_warm):

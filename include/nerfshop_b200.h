@@ -223,6 +223,13 @@ NsbStatus nsb_unpack_tiles(NsbContext* ctx, const float* src_packed_rgba_dev, co
                            int32_t width, int32_t height, int32_t rank, int32_t world,
                            float* fb_dev, float* depth_dev, void* stream);
 
+/* inverse for a whole all-gather result, ONE launch: rank k's packed float4 tiles start at gathered_rgba_dev + k*rank_stride_floats, its packed
+ * depth floats (gathered_depth_dev may be NULL) at gathered_depth_dev + k*rank_stride_floats — the two arrays may be the two halves of one gathered
+ * buffer. Every rank's tiles except skip_rank's (the caller's own, already in fb; -1 scatters all) are written into fb_dev / depth_dev.
+ * New (the reference is single-GPU): SURVEY.md section 8e. */
+NsbStatus nsb_unpack_gathered(NsbContext* ctx, const float* gathered_rgba_dev, const float* gathered_depth_dev, int32_t width, int32_t height,
+                              int32_t skip_rank, int32_t world, uint32_t rank_stride_floats, float* fb_dev, float* depth_dev, void* stream);
+
 /* ---- frame post-process: what Testbed::render_frame runs right after render_nerf ----------------- */
 /* reference: common.h:122-135 */
 typedef enum { NSB_COLOR_LINEAR = 0, NSB_COLOR_SRGB = 1, NSB_COLOR_VISPOSNEG = 2 } NsbColorSpace;

@@ -123,7 +123,7 @@ EXPORTED_SYMBOLS = [
     "nsb_update_density_grid", "nsb_download_density_grid", "nsb_cage_attach_mvc", "nsb_cage_deform", "nsb_cage_download",
     "nsb_poisson_boundary", "nsb_cage_set_membrane",
     "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
-    "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_accumulate", "nsb_tonemap",
+    "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_unpack_gathered", "nsb_accumulate", "nsb_tonemap",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
     "nsb_build_tet_grid", "nsb_compute_mvc", "nsb_interpolate_with_mvc", "nsb_local_rotations",
 ]
@@ -173,6 +173,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_tiles_for_rank.argtypes = [i32, i32, i32, i32, C.POINTER(u32)]
     lib.nsb_pack_tiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     lib.nsb_unpack_tiles.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.nsb_unpack_gathered.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.c_uint32, vp, vp, vp]
     lib.nsb_accumulate.argtypes = [vp, vp, vp, i32, i32, u32, i32, vp]
     lib.nsb_tonemap.argtypes = [vp, vp, vp, i32, i32, C.POINTER(NsbTonemap), vp]
     lib.nsb_inference.argtypes = [vp, vp, u32, vp, u32, vp]

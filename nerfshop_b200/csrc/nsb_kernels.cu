@@ -784,6 +784,21 @@ __global__ void k_pack_tiles(const float4* __restrict__ fb, const float* __restr
 	}
 }
 
+// all the OTHER ranks' shards of one all-gather -> the framebuffer (and depth), ONE launch: block = (local tile, source rank)
+__global__ void k_unpack_gathered(const float4* __restrict__ gathered, const float* __restrict__ gathered_depth, int W, int H, int tiles_x, int n_tiles, int skip_rank,
+                                  int world, uint32_t rank_stride /*floats between two ranks' shards, in BOTH arrays*/, float4* __restrict__ fb, float* __restrict__ depth) {
+	const uint32_t local = blockIdx.x, rank = blockIdx.y;
+	if ((int)rank == skip_rank) return;
+	const uint32_t tile = rank + local * (uint32_t)world;
+	if (tile >= (uint32_t)n_tiles) return;
+	const uint32_t lane = threadIdx.x;
+	const uint32_t px = (tile % (uint32_t)tiles_x) * TILE_W + (lane % TILE_W), py = (tile / (uint32_t)tiles_x) * TILE_H + (lane / TILE_W);
+	if (px >= (uint32_t)W || py >= (uint32_t)H) return;
+	const size_t p = (size_t)px + (size_t)W * py, q = (size_t)local * TILE_PIXELS + lane;
+	fb[p] = gathered[(size_t)rank * (rank_stride / 4) + q];
+	if (depth && gathered_depth) depth[p] = gathered_depth[(size_t)rank * rank_stride + q];
+}
+
 // =====================================================================================================
 // host side: context, uploads, C ABI
 // =====================================================================================================
@@ -1646,6 +1661,19 @@ extern "C" NsbStatus nsb_pack_tiles(NsbContext* c, const float* fb_dev, const fl
 extern "C" NsbStatus nsb_unpack_tiles(NsbContext* c, const float* src_rgba, const float* src_depth, int32_t W, int32_t H, int32_t rank, int32_t world,
                                       float* fb_dev, float* depth_dev, void* stream) {
 	return pack_impl(c, fb_dev, depth_dev, W, H, rank, world, const_cast<float*>(src_rgba), const_cast<float*>(src_depth), stream, 1);
+}
+
+extern "C" NsbStatus nsb_unpack_gathered(NsbContext* c, const float* gathered_rgba, const float* gathered_depth, int32_t W, int32_t H, int32_t skip_rank, int32_t world,
+                                         uint32_t rank_stride_floats, float* fb_dev, float* depth_dev, void* stream) {
+	if (!c || !gathered_rgba || !fb_dev || W <= 0 || H <= 0 || world <= 0) return fail(NSB_ERR_INVALID, "bad arguments");
+	CU(cudaSetDevice(c->device));
+	const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
+	const uint32_t need = (uint32_t)((tiles_x * tiles_y + world - 1) / world);
+	if (rank_stride_floats % 4 != 0 || rank_stride_floats < need * (uint32_t)TILE_PIXELS * 4u) return fail(NSB_ERR_INVALID, "rank stride %u floats is not a multiple of 4 or smaller than rank 0's %u tiles", rank_stride_floats, need);
+	k_unpack_gathered<<<dim3(need, (unsigned)world), TILE_PIXELS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(gathered_rgba), gathered_depth, W, H, tiles_x, tiles_x * tiles_y,
+	                                                                                         skip_rank, world, rank_stride_floats, reinterpret_cast<float4*>(fb_dev), depth_dev);
+	CU(cudaGetLastError());
+	return NSB_OK;
 }
 
 extern "C" NsbStatus nsb_accumulate(NsbContext* c, const float* frame, float* acc, int32_t W, int32_t H, uint32_t spp, int32_t color_space, void* stream) {

@@ -42,13 +42,18 @@ def unpack_numpy(shard: np.ndarray, W: int, H: int, rank: int, world: int, fb_fl
     fb_flat[idx[valid]] = shard[: idx.size][valid]
 
 
-def gather_framebuffer(renderer, fb, rank: int, world: int, shard, gathered):
-    """bench.py / a host's multi-GPU frame: pack own tiles, all-gather, unpack the other ranks' tiles into fb."""
+def gather_framebuffer(renderer, fb, rank: int, world: int, shard, gathered, depth=None):
+    """bench.py / a host's multi-GPU frame. RGBA and depth travel in ONE buffer: a shard row is 5 floats x 128 pixels per tile stored as
+    [tiles*128 float4 | tiles*128 float] (shard: float32 [tiles_per_shard*128*5], gathered: [world, tiles_per_shard*128*5]); one pack launch,
+    ONE all-gather, ONE unpack launch that scatters every other rank's tiles into fb and depth."""
     import torch.distributed as dist
 
-    renderer.pack_tiles(fb, None, rank, world, shard)
-    dist.all_gather_into_tensor(gathered, shard)
-    for k in range(world):
-        if k != rank:
-            renderer.unpack_tiles(gathered[k], None, k, world, fb)
+    n = shard.numel() // 5  # pixels per shard
+    rgba = shard[: 4 * n].view(n, 4)
+    dpt = shard[4 * n:] if depth is not None else None
+    renderer.pack_tiles(fb, depth, rank, world, rgba, dpt)
+    dist.all_gather_into_tensor(gathered, shard.view(1, -1))
+    g_rgba = gathered[:, : 4 * n]
+    g_depth = gathered[:, 4 * n:] if depth is not None else None
+    renderer.unpack_gathered(g_rgba, g_depth, gathered.stride(0), rank, world, fb, depth)
     return fb

@@ -209,6 +209,15 @@ class NerfRenderer:
         abi.check(self.lib, self.lib.nsb_unpack_tiles(self.ctx, packed_rgba.data_ptr(), 0 if packed_depth is None else packed_depth.data_ptr(), W, H, rank, world,
                                                       fb.data_ptr(), 0 if depth is None else depth.data_ptr(), s), "nsb_unpack_tiles")
 
+    def unpack_gathered(self, gathered_rgba, gathered_depth, rank_stride_floats, skip_rank, world, fb, depth=None):
+        """ONE launch: every rank's packed tiles of an all-gather result (rank k's float4 tiles at gathered_rgba + k*stride, its depth floats at
+        gathered_depth + k*stride) except skip_rank's -> fb (+ depth)."""
+        torch = _torch()
+        H, W = fb.shape[0], fb.shape[1]
+        s = torch.cuda.current_stream().cuda_stream
+        abi.check(self.lib, self.lib.nsb_unpack_gathered(self.ctx, gathered_rgba.data_ptr(), 0 if gathered_depth is None else gathered_depth.data_ptr(), W, H, skip_rank, world,
+                                                         int(rank_stride_floats), fb.data_ptr(), 0 if depth is None else depth.data_ptr(), s), "nsb_unpack_gathered")
+
     # ---- frame post-process (CudaRenderBuffer::accumulate / ::tonemap) ---------------------------------------
     def accumulate(self, frame_buffer, accumulate_buffer, spp: int, color_space: int = abi.NSB_COLOR_LINEAR):
         torch = _torch()

@@ -193,6 +193,17 @@ def test_tile_partition_union_equals_single(scene, renderer):
         torch.cuda.synchronize()
         assert torch.equal(acc, full) and torch.equal(dacc, dfull)
     assert total_rays == 2 * W * H
+    # the N > 1 frame of bench.py / parallel.gather_framebuffer: RGBA + depth of every rank in ONE gathered buffer, ONE unpack launch
+    for world in (2, 4):
+        n = renderer.tiles_for_rank(W, H, 0, world) * 128  # pixels per shard (rank 0 owns the most tiles)
+        gathered = torch.zeros((world, 5 * n), dtype=torch.float32, device="cuda")
+        for rank in range(world):
+            fb, depth = renderer.render(syn.make_frame(model, cam, W, H, rank=rank, world=world))
+            renderer.pack_tiles(fb, depth, rank, world, gathered[rank, : 4 * n].view(n, 4), gathered[rank, 4 * n:])
+        own, down = renderer.render(syn.make_frame(model, cam, W, H, rank=1, world=world))  # rank 1's view: its own tiles are in place already
+        renderer.unpack_gathered(gathered[:, : 4 * n], gathered[:, 4 * n:], gathered.stride(0), 1, world, own, down)
+        torch.cuda.synchronize()
+        assert torch.equal(own, full) and torch.equal(down, dfull)
 
 
 def test_full_size_properties(scene, renderer):
