@@ -36,6 +36,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """An experiment build next to the product library: lib/libnerfshop_b200_<name>.so with extra -D flags (tools/ only)."""
+    out = os.path.join(LIB_DIR, f"libnerfshop_b200_{name}.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-ccbin", ccbin] if ccbin else []) + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB

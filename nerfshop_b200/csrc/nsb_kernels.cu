@@ -455,6 +455,8 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	}
 }
 
+#include "nsb_render_ws.cuh"
+
 // =====================================================================================================
 // operator-level kernels (same device code as the fused renderer)
 // =====================================================================================================
@@ -856,6 +858,7 @@ struct NsbContext {
 	unsigned long long* d_stats = nullptr;
 	RayRec* d_list = nullptr;
 	size_t list_capacity = 0;
+	int use_ws = 1;                // frames without operators go through the warp-specialised kernel (NSB_WS=0: k_render_fused<false>)
 	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
 	int dda_budget = DDA_BUDGET;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;  // start, end, between k_prepare_rays and k_render_fused
@@ -968,6 +971,8 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 		CU(cudaFuncSetAttribute(k_render_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
 		CU(cudaFuncSetAttribute(k_render_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
 	}
+	CU(set_smem((const void*)k_render_ws, sizeof(ws::Smem), 1));
+	if (const char* e = getenv("NSB_WS")) c->use_ws = atoi(e) != 0;
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
 	if (const char* e = getenv("NSB_CHUNK")) { int v = atoi(e); if (v >= 0 && v <= 65535) c->refill_thr |= v << 8; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
@@ -1573,10 +1578,18 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		CU(cudaEventRecord(c->evm, stream));
 		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
 		if (grid > (my_tiles + NSB_TILES - 1) / NSB_TILES) grid = (uint32_t)((my_tiles + NSB_TILES - 1) / NSB_TILES);
-		auto kernel = (f.apply_ops && c->n_ops > 0) ? k_render_fused<true> : k_render_fused<false>;
+		const bool ops_on = f.apply_ops && c->n_ops > 0;
+		if (!ops_on && c->use_ws && (uint64_t)f.W * (uint64_t)f.H < (1ull << 28)) {  // k_render_ws ships the pixel in 28 bits of a flag word
+			uint32_t g2 = (uint32_t)c->sm_count;
+			if (g2 > (my_tiles + ws::PT - 1) / ws::PT) g2 = (uint32_t)((my_tiles + ws::PT - 1) / ws::PT);
+			k_render_ws<<<g2, ws::THREADS, sizeof(ws::Smem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list,
+			                                                           c->d_counters, c->d_counters + 1, c->d_stats, c->refill_thr, c->dda_budget);
+		} else {
+		auto kernel = ops_on ? k_render_fused<true> : k_render_fused<false>;
 		kernel<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
 		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
 		                                                          c->refill_thr, c->dda_budget);
+		}
 		CU(cudaGetLastError());
 	}
 	CU(cudaEventRecord(c->ev1, stream));

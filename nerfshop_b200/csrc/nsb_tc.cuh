@@ -58,6 +58,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -78,6 +81,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 			long long now = clock64();
 			if (t0 == 0) t0 = now;
 			else if (now - t0 > 4000000000ll) __trap();
+		}
+	}
+}
+// The same wait for a barrier whose completion is thousands of cycles away (the warp-specialised renderer's producer <-> consumer hand-offs):
+// a spinning warp takes issue slots from the warps it is waiting for, so back off with nanosleep between polls.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+	uint32_t addr = smem_u32(bar);
+	uint32_t done = 0;
+	long long t0 = 0;
+	for (uint32_t spins = 0;; ++spins) {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done)
+			: "r"(addr), "r"(parity)
+			: "memory");
+		if (done) break;
+		__nanosleep(ns);
+		if ((spins & 4095u) == 4095u) {
+			long long now = clock64();
+			if (t0 == 0) t0 = now;
+			else if (now - t0 > 8000000000ll) __trap();
 		}
 	}
 }
@@ -265,10 +291,13 @@ __device__ __forceinline__ void epilogue_hidden(uint8_t* a64, uint32_t tmem_row,
 //   dens[8]: the 16 fp16 outputs of the density MLP (packed half2), rgb[8]: the 16 outputs of the rgb MLP.
 // `dw` = this row's warped view direction; its 16 SH values are evaluated between L2 and L3.
 // `phase` is the running parity of the tile's mma_bar (one flip per layer).
-__device__ __forceinline__ void run_network(const TileCtx& c, uint32_t& phase, V3 dw, bool density_only, uint32_t* dens, uint32_t* rgb) {
+// `a_first`: shared-window address of the first layer's operand when it does not live in c.a32 (the warp-specialised renderer's producers
+// write the grid features into their own double-buffered operand); 0 = c.a32.
+__device__ __forceinline__ void run_network(const TileCtx& c, uint32_t& phase, V3 dw, bool density_only, uint32_t* dens, uint32_t* rgb, uint32_t a_first = 0) {
 	const uint32_t row = c.row;
 	const uint32_t tmem_row = c.tmem + ((row & ~31u) << 16);  // lane field = first lane of this warp's quarter
 	const uint32_t a32 = smem_u32(c.a32), a64 = smem_u32(c.a64), w = c.w_addr;
+	if (a_first == 0) a_first = a32;
 #define NSB_SYNC_ISSUE(N_, K_, A_, W_)                                  \
 	fence_async_smem();                                                 \
 	tc_fence_before();                                                  \
@@ -277,7 +306,7 @@ __device__ __forceinline__ void run_network(const TileCtx& c, uint32_t& phase, V
 	mbar_wait(c.mma_bar, phase); phase ^= 1;                            \
 	tc_fence_after();
 
-	NSB_SYNC_ISSUE(64, 32, a32, W1_OFF)   // L1: a32 (32) -> 64
+	NSB_SYNC_ISSUE(64, 32, a_first, W1_OFF)   // L1: grid features (32) -> 64
 	epilogue_hidden(c.a64, tmem_row, row);
 	NSB_SYNC_ISSUE(16, 64, a64, W2_OFF)   // L2: a64 (64) -> 16
 	{
