@@ -858,7 +858,7 @@ struct NsbContext {
 	unsigned long long* d_stats = nullptr;
 	RayRec* d_list = nullptr;
 	size_t list_capacity = 0;
-	int use_ws = 1;                // frames without operators go through the warp-specialised kernel (NSB_WS=0: k_render_fused<false>)
+	int use_ws = 0;                // NSB_WS=1: frames without operators go through the warp-specialised kernel (experimental; default k_render_fused<false>)
 	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
 	int dda_budget = DDA_BUDGET;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;  // start, end, between k_prepare_rays and k_render_fused

@@ -29,16 +29,18 @@ constexpr int PT = NSB_WS_PT;         // producer tiles (128 ray slots each)
 constexpr int CG = NSB_WS_CG;         // consumer groups (128 threads each)
 constexpr int TPG = PT / CG;          // producer tiles per consumer group
 constexpr int THREADS = (PT + CG) * 128;
-constexpr uint32_t TMEM_COLS_TOTAL = CG <= 1 ? 64 : CG <= 2 ? 128 : CG <= 4 ? 256 : 512;  // 64 accumulator columns per consumer group (power of two)
-static_assert(PT % CG == 0, "every consumer group serves PT / CG producer tiles");
+constexpr uint32_t TMEM_COLS_TOTAL = CG * TPG * 64 <= 64 ? 64 : CG * TPG * 64 <= 128 ? 128 : CG * TPG * 64 <= 256 ? 256 : 512;  // 64 accumulator columns per producer tile
+static_assert(PT == 2 * CG, "a consumer group walks the layer chain for TWO producer tiles at once");
 
 enum { F_SAMPLE = 1u, F_FIRST = 2u, F_EXIT = 4u, F_DROP = 8u };
 enum { S_PX = 0, S_PY, S_PZ, S_DT, S_DX, S_DY, S_DZ, S_FLAGS, S_FIELDS };  // per sample: warped position, warped dt, warped direction, flags (F_FIRST: S_DT holds the pixel)
 // consumer-side ray state, parked in shared memory between generations (a group alternates between two tiles)
 enum { A_CR = 0, A_CG, A_CB, A_CA, A_DEPTH, A_MAXW, A_PIX, A_META, A_FIELDS };  // META: bit 31 alive, low bits n_steps
 
-struct Tile {
-	uint8_t feat[2][tc::A32_BYTES];
+struct __align__(128) Tile {  // the UMMA descriptors address feat in 16-byte units
+	uint8_t feat[tc::A32_BYTES];           // ONE operand buffer: released (feat_free) as soon as the first layer's MMAs have completed, long before the generation is done
+	uint32_t out[3][128];                  // network outputs the composite needs: density raw | (r, g) | (b, -) as packed fp16
+	uint64_t feat_free;
 	uint32_t side[2][S_FIELDS][128];
 	float acc[A_FIELDS][128];
 	uint32_t died_epoch[128];
@@ -47,8 +49,8 @@ struct Tile {
 	uint32_t stop, epoch_pad[3];
 	uint32_t cepoch[128];  // consumer's ray counter per slot
 };
-struct Group {
-	uint8_t a64[tc::A64_BYTES];
+struct __align__(128) Group {
+	uint8_t a64[TPG][tc::A64_BYTES];
 	uint64_t mma_bar;
 	uint64_t pad[15];
 };
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(ws::THREADS, 1) k_render_ws(const DevFrame f, 
 		tc::mbar_init(&S.w_bar, 1);
 		for (int t = 0; t < PT; ++t) {
 			for (int b = 0; b < 2; ++b) { tc::mbar_init(&S.tile[t].full[b], 4); tc::mbar_init(&S.tile[t].empty[b], 4); }
+			tc::mbar_init(&S.tile[t].feat_free, 1);
 			S.tile[t].stop = 0;
 		}
 		for (int g = 0; g < CG; ++g) tc::mbar_init(&S.grp[g].mma_bar, 1);
@@ -188,7 +191,8 @@ __global__ void __launch_bounds__(ws::THREADS, 1) k_render_ws(const DevFrame f, 
 				++n_steps;
 				flags |= F_SAMPLE;
 			}
-			encode_to_a32(TL.feat[b], m, has_sample, pw, slot);
+			if (g >= 1) tc::mbar_wait_backoff(&TL.feat_free, (g - 1u) & 1u, 50);  // the first layer of generation g - 1 has read the operand
+			encode_to_a32(TL.feat, m, has_sample, pw, slot);
 			if (flags & (F_SAMPLE | F_FIRST)) {
 				const V3 dw = warp_direction(rd);
 				TL.side[b][S_PX][slot] = __float_as_uint(pw.x); TL.side[b][S_PY][slot] = __float_as_uint(pw.y); TL.side[b][S_PZ][slot] = __float_as_uint(pw.z);
@@ -212,47 +216,127 @@ __global__ void __launch_bounds__(ws::THREADS, 1) k_render_ws(const DevFrame f, 
 #endif
 	} else {
 		// =============================================== consumer ===============================================
+		// A group walks the five layers for its TWO producer tiles together: per layer one tile barrier, both tiles' MMAs issued back to back
+		// with one completion wait, then both epilogues — half the barriers and waits per sample of the one-tile chain.
 		const uint32_t grp = warp >> 2, row = threadIdx.x & 127u;
 		Group& G = S.grp[grp];
+		Tile& TA = S.tile[grp * TPG + 0];
+		Tile& TB = S.tile[grp * TPG + 1];
 		tc::mbar_wait(&S.w_bar, 0);
-		tc::TileCtx C;
-		C.a32 = G.a64; C.a64 = G.a64; C.w_addr = tc::smem_u32(S.w); C.mma_bar = &G.mma_bar; C.tmem = tmem_base + grp * tc::TMEM_COLS; C.row = row;
-		C.bar_id = 1 + grp;
-		uint32_t phase = 0, done_mask = 0;
+		const uint32_t w_addr = tc::smem_u32(S.w);
+		const uint32_t tmemA = tmem_base + (grp * TPG + 0) * tc::TMEM_COLS, tmemB = tmem_base + (grp * TPG + 1) * tc::TMEM_COLS;
+		const uint32_t lane_field = (row & ~31u) << 16;
+		const uint32_t a64A = tc::smem_u32(G.a64[0]), a64B = tc::smem_u32(G.a64[1]);
+		const uint32_t featA = tc::smem_u32(TA.feat), featB = tc::smem_u32(TB.feat);
+		const uint32_t bar_id = 1 + grp;
+		uint32_t phase = 0;
 		const float sat = 1.0f - f.min_T;
 		const V3 cam_fwd = v3(f.cam1[6], f.cam1[7], f.cam1[8]);
+		// one layer for both tiles: D_A = A_A W^T, D_B = A_B W^T; `release` = also arrive on the tiles' feat_free barriers (first layer)
+		auto layer = [&](auto n_tag, auto k_tag, uint32_t aA, uint32_t aB, uint32_t w_off, bool release) {
+			constexpr uint32_t N = decltype(n_tag)::value, K = decltype(k_tag)::value;
+			tc::fence_async_smem();
+			tc::tc_fence_before();
+			asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+			if (row < 32) {
+				if (row == 0) {
+					tc::tc_fence_after();
+					constexpr uint32_t idesc = tc::make_idesc(tc::ROWS, N);
+#pragma unroll
+					for (uint32_t k = 0; k < K / 16; ++k)
+						tc::umma_f16(tmemA, tc::make_desc(aA + k * 2 * (tc::ROWS * 16), tc::ROWS * 16, 128), tc::make_desc(w_addr + w_off + k * 2 * (N * 16), N * 16, 128), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+					for (uint32_t k = 0; k < K / 16; ++k)
+						tc::umma_f16(tmemB, tc::make_desc(aB + k * 2 * (tc::ROWS * 16), tc::ROWS * 16, 128), tc::make_desc(w_addr + w_off + k * 2 * (N * 16), N * 16, 128), idesc, k > 0 ? 1u : 0u);
+					tc::umma_commit(&G.mma_bar);
+				}
+				__syncwarp();
+			}
+			tc::mbar_wait(&G.mma_bar, phase);
+			phase ^= 1;
+			tc::tc_fence_after();
+			if (release && row == 0) { tc::mbar_arrive(&TA.feat_free); tc::mbar_arrive(&TB.feat_free); }  // the MMAs have read the producers' operands
+		};
+		using I16 = std::integral_constant<uint32_t, 16>;
+		using I32 = std::integral_constant<uint32_t, 32>;
+		using I64 = std::integral_constant<uint32_t, 64>;
 		for (uint32_t g = 0;; ++g) {
 			const uint32_t b = g & 1u;
-			bool any = false;
+#ifdef NSB_PROFILE
+			const long long q0 = clock64();
+#endif
+			tc::mbar_wait_backoff(&TA.full[b], (g >> 1) & 1u, 100);
+			tc::mbar_wait_backoff(&TB.full[b], (g >> 1) & 1u, 100);
+#ifdef NSB_PROFILE
+			const long long q1 = clock64();
+			cyc_wait += q1 - q0;
+#endif
+			{
+				const volatile uint32_t* fa = TA.fin[b];
+				const volatile uint32_t* fbn = TB.fin[b];
+				if (fa[0] + fa[1] + fa[2] + fa[3] + fbn[0] + fbn[1] + fbn[2] + fbn[3] == 8u) {  // both tiles out of rays: this and all later generations are empty
+					if (row == 0) {
+						*reinterpret_cast<volatile uint32_t*>(&TA.stop) = 1u; *reinterpret_cast<volatile uint32_t*>(&TB.stop) = 1u;
+						tc::mbar_arrive(&TA.feat_free); tc::mbar_arrive(&TB.feat_free);  // no first layer this generation: release the producers that already wait for it
+					}
+					__syncwarp();
+					if (lane == 0) { tc::mbar_arrive(&TA.empty[b]); tc::mbar_arrive(&TB.empty[b]); }
+					break;
+				}
+			}
+			if (row == 0) ++n_gen;
+			// ---- the five layers, both tiles ----
+			layer(I64{}, I32{}, featA, featB, tc::W1_OFF, true);
+			tc::epilogue_hidden(G.a64[0], tmemA + lane_field, row);
+			tc::epilogue_hidden(G.a64[1], tmemB + lane_field, row);
+			layer(I16{}, I64{}, a64A, a64B, tc::W2_OFF, false);
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {  // density MLP output (16) + SH(direction) (16) = the rgb network's input, in place
+				Tile& TL = k ? TB : TA;
+				uint32_t r[16];
+				tc::tmem_ld16((k ? tmemB : tmemA) + lane_field, r);
+				tc::tmem_wait_ld();
+				uint32_t d[8];
+#pragma unroll
+				for (int i = 0; i < 8; ++i) d[i] = tc::pack(r[2 * i], r[2 * i + 1]);
+				TL.out[0][row] = d[0];
+				const V3 dw = v3(__uint_as_float(TL.side[b][S_DX][row]), __uint_as_float(TL.side[b][S_DY][row]), __uint_as_float(TL.side[b][S_DZ][row]));
+				__half2 sh[8];
+				encode_sh4(dw, sh);
+				uint8_t* a32 = G.a64[k];
+				tc::store_chunk(a32, 0, row, make_uint4(d[0], d[1], d[2], d[3]));
+				tc::store_chunk(a32, 1, row, make_uint4(d[4], d[5], d[6], d[7]));
+				tc::store_chunk(a32, 2, row, make_uint4(tc::pack_h2(sh[0]), tc::pack_h2(sh[1]), tc::pack_h2(sh[2]), tc::pack_h2(sh[3])));
+				tc::store_chunk(a32, 3, row, make_uint4(tc::pack_h2(sh[4]), tc::pack_h2(sh[5]), tc::pack_h2(sh[6]), tc::pack_h2(sh[7])));
+			}
+			layer(I64{}, I32{}, a64A, a64B, tc::W3_OFF, false);
+			tc::epilogue_hidden(G.a64[0], tmemA + lane_field, row);
+			tc::epilogue_hidden(G.a64[1], tmemB + lane_field, row);
+			layer(I64{}, I64{}, a64A, a64B, tc::W4_OFF, false);
+			tc::epilogue_hidden(G.a64[0], tmemA + lane_field, row);
+			tc::epilogue_hidden(G.a64[1], tmemB + lane_field, row);
+			layer(I16{}, I64{}, a64A, a64B, tc::W5_OFF, false);
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				uint32_t r[4];
+				tc::tmem_ld4((k ? tmemB : tmemA) + lane_field, r);
+				tc::tmem_wait_ld();
+				Tile& TL = k ? TB : TA;
+				TL.out[1][row] = tc::pack(r[0], r[1]);
+				TL.out[2][row] = tc::pack(r[2], r[3]);
+			}
+			tc::tc_fence_before();
+			// ---- composite (composite_kernel_nerf :750-955) + shade (shade_kernel_nerf :2464-2482), one tile after the other ----
 #pragma unroll 1
 			for (uint32_t k = 0; k < (uint32_t)TPG; ++k) {
-				if ((done_mask >> k) & 1u) continue;
-				any = true;
 				Tile& TL = S.tile[grp * TPG + k];
-#ifdef NSB_PROFILE
-				const long long q0 = clock64();
-#endif
-				tc::mbar_wait_backoff(&TL.full[b], (g >> 1) & 1u, 100);
-#ifdef NSB_PROFILE
-				const long long q1 = clock64();
-				cyc_wait += q1 - q0;
-#endif
-				const volatile uint32_t* fin = TL.fin[b];
-				if (fin[0] + fin[1] + fin[2] + fin[3] == 4u) {  // every producer warp of the tile is out of rays: this and all later generations are empty
-					done_mask |= 1u << k;
-					if (row == 0) *reinterpret_cast<volatile uint32_t*>(&TL.stop) = 1u;
-					__syncwarp();
-					if (lane == 0) tc::mbar_arrive(&TL.empty[b]);
-					continue;
-				}
-				if (k == 0 && row == 0) ++n_gen;
 				const uint32_t fl = TL.side[b][S_FLAGS][row];
 				const uint32_t flags = fl & 15u;
 				uint32_t meta = __float_as_uint(TL.acc[A_META][row]);
 				uint32_t pix = __float_as_uint(TL.acc[A_PIX][row]);
 				bool fresh = false;
 				if (flags & F_FIRST) {
-					pix = fl >> 4;  // pixels < 2^28 (nsb_render rejects larger frames)
+					pix = fl >> 4;  // pixels < 2^28 (the launcher falls back to k_render_fused for larger frames)
 					TL.acc[A_PIX][row] = __uint_as_float(pix);
 					meta = 0x80000000u;
 					TL.cepoch[row] = TL.cepoch[row] + 1u;
@@ -261,15 +345,11 @@ __global__ void __launch_bounds__(ws::THREADS, 1) k_render_ws(const DevFrame f, 
 				bool alive = (meta >> 31) != 0u;
 				uint32_t n_steps = meta & 0x7fffffffu;
 				const bool has_sample = alive && (flags & F_SAMPLE);
-				const V3 dw = v3(__uint_as_float(TL.side[b][S_DX][row]), __uint_as_float(TL.side[b][S_DY][row]), __uint_as_float(TL.side[b][S_DZ][row]));
-				uint32_t dens[8], rgbo[8];
-				tc::run_network(C, phase, dw, false, dens, rgbo, tc::smem_u32(TL.feat[b]));
 				float cr = 0.0f, cg = 0.0f, cb = 0.0f, ca = 0.0f, ray_depth = 0.0f, max_weight = 0.0f;
 				if (!fresh) {
 					cr = TL.acc[A_CR][row]; cg = TL.acc[A_CG][row]; cb = TL.acc[A_CB][row]; ca = TL.acc[A_CA][row];
 					ray_depth = TL.acc[A_DEPTH][row]; max_weight = TL.acc[A_MAXW][row];
 				}
-				// shade_kernel_nerf (:2464-2482) for a finished ray (compact_kernel_nerf :2503 filter)
 				auto finish = [&](bool left_aabb, float r_, float g_, float b_, float a_) {
 					alive = false;
 					if (!(a_ > 0.001f)) return;
@@ -286,18 +366,19 @@ __global__ void __launch_bounds__(ws::THREADS, 1) k_render_ws(const DevFrame f, 
 					fb[pix] = make_float4(__fmaf_rn(prev.x, om, r), __fmaf_rn(prev.y, om, gg), __fmaf_rn(prev.z, om, bb), __fmaf_rn(prev.w, om, a));
 					if (a > 0.2f) depth_out[pix] = ray_depth;
 				};
-				if (has_sample) {  // composite_kernel_nerf :750-955 for this one sample
+				if (has_sample) {
 					++n_steps;
 					++c_samples;
 					const V3 pw = v3(__uint_as_float(TL.side[b][S_PX][row]), __uint_as_float(TL.side[b][S_PY][row]), __uint_as_float(TL.side[b][S_PZ][row]));
 					const float dtw = __uint_as_float(TL.side[b][S_DT][row]);
+					const uint32_t o0 = TL.out[0][row], o1 = TL.out[1][row], o2 = TL.out[2][row];
 					const V3 cpos = unwarp_position(pw, f.tmin, f.tmax);
 					const float T = 1.0f - ca;
 					const float dtu = unwarp_dt(dtw);
-					const float sigma = network_to_density(h_lo(dens[0]), f.density_act);
+					const float sigma = network_to_density(h_lo(o0), f.density_act);
 					const float alpha = 1.0f - __expf(-sigma * dtu);
 					const float weight = alpha * T;
-					float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
+					float rgb[3] = {network_to_rgb(h_lo(o1), f.rgb_act), network_to_rgb(h_hi(o1), f.rgb_act), network_to_rgb(h_lo(o2), f.rgb_act)};
 					if (f.mode != NSB_RENDER_SHADE) {
 						V3 ro = v3(f.cam1[9], f.cam1[10], f.cam1[11]);
 						if (f.mode == NSB_RENDER_DEPTH || f.mode == NSB_RENDER_DISTANCE) {  // the ray origin (rolling shutter: per pixel), debug modes only
@@ -333,11 +414,10 @@ __global__ void __launch_bounds__(ws::THREADS, 1) k_render_ws(const DevFrame f, 
 				TL.acc[A_META][row] = __uint_as_float((alive ? 0x80000000u : 0u) | (n_steps & 0x7fffffffu));
 				__syncwarp();
 				if (lane == 0) tc::mbar_arrive(&TL.empty[b]);
-#ifdef NSB_PROFILE
-				cyc_work += clock64() - q1;
-#endif
 			}
-			if (!any) break;
+#ifdef NSB_PROFILE
+			cyc_work += clock64() - q1;
+#endif
 		}
 #ifdef NSB_PROFILE
 		if (threadIdx.x == 0) { atomicAdd(stats + ST_CYC_MLP, (unsigned long long)cyc_wait); atomicAdd(stats + ST_CYC_COMPOSITE, (unsigned long long)cyc_work); }
