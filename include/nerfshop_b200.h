@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NSB_ABI_VERSION 1
+#define NSB_ABI_VERSION 2
 
 /* reference: common_nerf.h:16-39 */
 #define NSB_NERF_GRIDSIZE 128u
@@ -109,10 +109,13 @@ typedef struct {
 	int32_t  apply_operators;          /* m_enable_edits && !m_distill */
 	int32_t  poisson_target;           /* NerfTracer::m_poisson_target */
 	int32_t  linear_colors;            /* m_nerf.training.linear_colors */
-	int32_t  min_mip;                  /* (show_accel>=0) ? show_accel : 0 */
+	int32_t  min_mip;                  /* (show_accel>=0) ? show_accel : 0: the coarsest occupancy cascade the march may test (:2750, :2849) */
 	/* image-plane partition (new; the reference is single-GPU): this context renders the
 	 * 16x8-pixel tiles whose linear index t satisfies t % tile_world == tile_rank. */
 	int32_t  tile_rank, tile_world;
+	/* m_nerf.show_accel >= 0 (the GUI's occupancy-grid visualisation): 0 = off (the reference's -1); 1 = on with show_accel = min_mip: every sample's
+	 * alpha is forced to 1 (testbed_nerf.cu:788-790) and Positions mode colours the occupancy cells (:913-923). Zero-initialised frames have it off. */
+	int32_t  show_accel;
 } NsbFrame;
 
 typedef enum { NSB_OP_CAGE = 0, NSB_OP_AFFINE = 1 } NsbEditOpType;
@@ -185,6 +188,13 @@ NsbStatus   nsb_destroy(NsbContext* ctx);
 NsbStatus nsb_model_n_params(const NsbModelDesc* desc, uint64_t* n_params);
 /* replaces tcnn::Trainer::deserialize -> NerfNetwork::set_params (testbed.cu:3087). */
 NsbStatus nsb_upload_model(NsbContext* ctx, const NsbModelDesc* desc, const uint16_t* params_fp16, uint64_t n_params);
+/* Accumulator policy of the two fully fused MLPs (every entry point that evaluates the network). The reference's tiny-cuda-nn FullyFusedMLP
+ * runs wmma m16n16k16 with __half accumulator fragments (the submodule is absent, so this is not verifiable here):
+ *   NSB_MLP_ACC_F32 (default) fp32 accumulators in TMEM, one rounding to fp16 per layer output;
+ *   NSB_MLP_ACC_F16 fp16 accumulators in TMEM: the running sum is rounded to fp16 by every K=16 tcgen05.mma, as with __half fragments.
+ * The two differ by up to 1e-2 in RGBA on 0.02 % of the pixels of a 480x270 frame (tests/test_mlp_policy.py). */
+typedef enum { NSB_MLP_ACC_F32 = 0, NSB_MLP_ACC_F16 = 1 } NsbMlpAccumulator;
+NsbStatus nsb_set_mlp_accumulator(NsbContext* ctx, int32_t policy);
 /* replaces Testbed::Nerf::density_grid_bitfield (testbed.h:626; built at testbed.cu:3079). */
 NsbStatus nsb_upload_occupancy(NsbContext* ctx, const uint8_t* bitfield, uint64_t n_bytes);
 /* replaces Testbed::update_density_grid_mean_and_bitfield (testbed_nerf.cu:3642-3658: mean of cascade 0, grid_to_bitfield :514,
@@ -192,6 +202,10 @@ NsbStatus nsb_upload_occupancy(NsbContext* ctx, const uint8_t* bitfield, uint64_
  * density_grid: HOST float[5*128^3]; the resulting bitfield becomes the context's occupancy and, if bitfield_out != NULL,
  * is also copied back (NSB_BITFIELD_BYTES). */
 NsbStatus nsb_upload_density_grid(NsbContext* ctx, const float* density_grid, uint64_t n_floats, uint8_t* bitfield_out);
+/* The same two uploads from DEVICE memory (the reference owns both on the device: tcnn::Trainer::params(), Testbed::Nerf::density_grid_bitfield):
+ * the 26 MB hash table is copied device-to-device; only the 20 KB of MLP weights pass through the host to be laid out as tensor-core operands. */
+NsbStatus nsb_upload_model_dev(NsbContext* ctx, const NsbModelDesc* desc, const uint16_t* params_fp16_dev, uint64_t n_params);
+NsbStatus nsb_upload_occupancy_dev(NsbContext* ctx, const uint8_t* bitfield_dev, uint64_t n_bytes);
 /* replaces NerfTracer::{add,delete,reset}_edit_operator; list order = m_edit_operators order
  * (operators are applied in REVERSE list order, testbed_nerf.cu:2868,2899). n = 0 clears. */
 NsbStatus nsb_set_edit_ops(NsbContext* ctx, const NsbEditOp* ops, int32_t n);
@@ -294,6 +308,18 @@ NsbStatus nsb_map_rays(NsbContext* ctx, float* coords_dev, uint8_t* empty_mask_d
  * n samples: sh_dev [27*n], out_density_dev [n], residual_density_dev [n] (cleared first, like :2863-2866). */
 NsbStatus nsb_poisson_residuals(NsbContext* ctx, const float* coords_dev, uint32_t n,
                                 float* sh_dev, float* out_density_dev, float* residual_density_dev, void* stream);
+/* ONE operator of the uploaded list (op_index >= 0) = one call of the EditOperator virtual (edit_operator.h:43,45,68,81); outputs are not cleared,
+ * like the virtuals. op_index < 0 = the reference's loop over all operators in reverse order with its clears (the two functions above).
+ *   nsb_map_rays_op                 EditOperator::map_rays                          (interpolate_tet / translate_in_box)
+ *   nsb_poisson_residuals_op        EditOperator::compute_poisson_full_residuals   (compute_residual_poisson_kernel)
+ *   nsb_map_positions               EditOperator::map_positions                    (interpolate_tet_pos / translate_in_box_pos; PitchedPtr<NerfPosition>: stride in floats)
+ *   nsb_poisson_residual_density    EditOperator::compute_poisson_residual_density (density_fp16[i] += (half) interpolated residual density) */
+NsbStatus nsb_map_rays_op(NsbContext* ctx, int32_t op_index, float* coords_dev, uint8_t* empty_mask_dev, uint32_t n, void* stream);
+NsbStatus nsb_poisson_residuals_op(NsbContext* ctx, int32_t op_index, const float* coords_dev, uint32_t n, float* sh_dev, float* out_density_dev,
+                                   float* residual_density_dev, void* stream);
+NsbStatus nsb_map_positions(NsbContext* ctx, int32_t op_index, float* positions_dev, uint32_t stride_floats, uint8_t* empty_mask_dev, uint32_t n, void* stream);
+NsbStatus nsb_poisson_residual_density(NsbContext* ctx, int32_t op_index, const float* positions_dev, uint32_t stride_floats, uint16_t* density_fp16_dev,
+                                       uint32_t n, void* stream);
 /* Occupancy march alone (init_rays + advance_pos + generate_next loop with no termination):
  * for each listed pixel writes up to max_samples {t, dt, pos3, mip, cell_idx} records and the count.
  * rec_dev: float[n_pixels*max_samples*5] (t,dt,x,y,z), idx_dev: uint32[n_pixels*max_samples*2] (mip, cell),

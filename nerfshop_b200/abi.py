@@ -11,7 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnerfshop_b200.so")
 
-NSB_ABI_VERSION = 1
+NSB_ABI_VERSION = 2
+NSB_MLP_ACC_F32, NSB_MLP_ACC_F16 = 0, 1
 NSB_NERF_GRIDSIZE = 128
 NSB_NERF_CASCADES = 5
 NSB_GRID_CELLS = NSB_NERF_CASCADES * NSB_NERF_GRIDSIZE ** 3
@@ -54,7 +55,7 @@ class NsbFrame(C.Structure):
         ("rgb_activation", i32), ("density_activation", i32), ("render_mode", i32),
         ("spp_index", u32), ("snap_to_pixel_centers", i32), ("apply_operators", i32),
         ("poisson_target", i32), ("linear_colors", i32), ("min_mip", i32),
-        ("tile_rank", i32), ("tile_world", i32),
+        ("tile_rank", i32), ("tile_world", i32), ("show_accel", i32),
     ]
 
 
@@ -119,12 +120,13 @@ class NsbRenderStats(C.Structure):
 # every symbol include/nerfshop_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTED_SYMBOLS = [
     "nsb_abi_version", "nsb_last_error", "nsb_create", "nsb_destroy",
-    "nsb_model_n_params", "nsb_upload_model", "nsb_upload_occupancy", "nsb_upload_density_grid", "nsb_set_edit_ops",
+    "nsb_model_n_params", "nsb_set_mlp_accumulator", "nsb_upload_model", "nsb_upload_model_dev", "nsb_upload_occupancy_dev", "nsb_upload_occupancy", "nsb_upload_density_grid", "nsb_set_edit_ops",
     "nsb_update_density_grid", "nsb_download_density_grid", "nsb_cage_attach_mvc", "nsb_cage_deform", "nsb_cage_download",
     "nsb_poisson_boundary", "nsb_cage_set_membrane",
     "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
     "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_unpack_gathered", "nsb_accumulate", "nsb_tonemap",
-    "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_march_trace",
+    "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_map_rays_op", "nsb_poisson_residuals_op",
+    "nsb_map_positions", "nsb_poisson_residual_density", "nsb_march_trace",
     "nsb_build_tet_grid", "nsb_compute_mvc", "nsb_interpolate_with_mvc", "nsb_local_rotations",
 ]
 
@@ -156,6 +158,13 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_destroy.argtypes = [vp]
     lib.nsb_model_n_params.argtypes = [C.POINTER(NsbModelDesc), C.POINTER(u64)]
     lib.nsb_upload_model.argtypes = [vp, C.POINTER(NsbModelDesc), vp, u64]
+    lib.nsb_set_mlp_accumulator.argtypes = [vp, i32]
+    lib.nsb_upload_model_dev.argtypes = [vp, C.POINTER(NsbModelDesc), vp, u64]
+    lib.nsb_upload_occupancy_dev.argtypes = [vp, vp, u64]
+    lib.nsb_map_rays_op.argtypes = [vp, i32, vp, vp, u32, vp]
+    lib.nsb_poisson_residuals_op.argtypes = [vp, i32, vp, u32, vp, vp, vp, vp]
+    lib.nsb_map_positions.argtypes = [vp, i32, vp, u32, vp, u32, vp]
+    lib.nsb_poisson_residual_density.argtypes = [vp, i32, vp, u32, vp, u32, vp]
     lib.nsb_upload_occupancy.argtypes = [vp, vp, u64]
     lib.nsb_upload_density_grid.argtypes = [vp, vp, u64, vp]
     lib.nsb_update_density_grid.argtypes = [vp, C.POINTER(NsbGridUpdate), vp]

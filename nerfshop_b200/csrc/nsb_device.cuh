@@ -54,7 +54,7 @@ struct DevFrame {
 	int rgb_act, density_act, mode;
 	uint32_t spp;
 	float pix_off[2];  // ld_random_pixel_offset(snap ? 0 : spp), pixel independent -> computed on the host
-	int apply_ops, poisson_target, linear_colors, min_mip;
+	int apply_ops, poisson_target, linear_colors, min_mip, show_accel;
 	int tile_rank, tile_world;
 	int tiles_x, tiles_y;
 };

@@ -154,7 +154,8 @@ constexpr uint32_t RENDER_TMEM_COLS = NSB_TILES <= 1 ? 64 : NSB_TILES <= 2 ? 128
 
 // OPS = false: the instantiation for frames without edit operators (f.apply_ops == 0 or no operator uploaded) carries none of the deform /
 // membrane code in its hot loop (the loop has to fit the instruction cache: profiles/README.md item 6).
-template <bool OPS>
+// ACC16: the MLP accumulator policy (nsb_set_mlp_accumulator): fp16 TMEM accumulators, like the reference's wmma __half fragments.
+template <bool OPS, bool ACC16>
 __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
                                                       float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 #ifdef NSB_PROFILE
 			enc_cycles += clock64() - e0;
 #endif
-			tc::run_network(C, phase, dw, old_pass, dens, rgbo);
+			tc::run_network<ACC16>(C, phase, dw, old_pass, dens, rgbo);
 			if (old_pass) {
 				sigma_old_raw = h_lo(dens[0]);
 				if (need_old) ++c_old;
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 // operator-level kernels (same device code as the fused renderer)
 // =====================================================================================================
 // NerfNetwork::inference_mixed_precision / ::density on a flat batch: one CTA = 128 samples.
-template <bool DENSITY_ONLY>
+template <bool DENSITY_ONLY, bool ACC16>
 __global__ void __launch_bounds__(128) k_inference(const DevModel m, const float* __restrict__ coords, uint32_t n, __half* __restrict__ out,
                                                    uint32_t n_padded) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(128) k_inference(const DevModel m, const float
 		}
 		uint32_t dens[8], rgbo[8];
 		encode_to_a32(S.a32, m, valid, pw, tid);
-		tc::run_network(tc::single_tile_ctx(S, tmem_base), phase, dw, DENSITY_ONLY, dens, rgbo);
+		tc::run_network<ACC16>(tc::single_tile_ctx(S, tmem_base), phase, dw, DENSITY_ONLY, dens, rgbo);
 		if (i < n_padded) {
 			const uint32_t* src = DENSITY_ONLY ? dens : rgbo;
 #pragma unroll
@@ -513,6 +514,7 @@ __global__ void __launch_bounds__(256) k_encode(const DevModel m, const float* _
 	}
 }
 
+// EditOperator::map_rays for operators [0, n_ops) of `ops` in reverse order; the mask is only ever SET (the caller clears it, testbed_nerf.cu:2898)
 __global__ void k_map_rays(const DevOp* __restrict__ ops, int n_ops, float* __restrict__ coords, uint8_t* __restrict__ empty_mask, uint32_t n) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -522,18 +524,80 @@ __global__ void k_map_rays(const DevOp* __restrict__ ops, int n_ops, float* __re
 	map_one(ops, n_ops, pw, dw, empty);
 	coords[7 * (size_t)i] = pw.x; coords[7 * (size_t)i + 1] = pw.y; coords[7 * (size_t)i + 2] = pw.z;
 	coords[7 * (size_t)i + 4] = dw.x; coords[7 * (size_t)i + 5] = dw.y; coords[7 * (size_t)i + 6] = dw.z;
-	empty_mask[i] = empty ? 1 : 0;
+	if (empty) empty_mask[i] = 1;
 }
 
+// EditOperator::compute_poisson_full_residuals: outputs are written only where an operator's tet contains the sample (the caller clears, :2863-2866)
 __global__ void k_poisson(const DevOp* __restrict__ ops, int n_ops, const float* __restrict__ coords, uint32_t n, float* __restrict__ sh,
                           float* __restrict__ od, float* __restrict__ rd) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	Membrane mem;
 	poisson_one(ops, n_ops, v3(coords[7 * (size_t)i], coords[7 * (size_t)i + 1], coords[7 * (size_t)i + 2]), mem);
+	if (mem.op < 0) return;
 	od[i] = mem.dob;
 	rd[i] = mem.drb;
-	for (int k = 0; k < 27; ++k) sh[27 * (size_t)i + k] = mem.op >= 0 ? membrane_sh(ops, mem, k) : 0.0f;
+	for (int k = 0; k < 27; ++k) sh[27 * (size_t)i + k] = membrane_sh(ops, mem, k);
+}
+
+// EditOperator::map_positions: interpolate_tet_pos (cage_deformation.cu:136-192: no direction, and the vacated-region mask does NOT look at `copy`)
+// and translate_in_box_pos (affine_duplication.cu:69-90), operators [0, n_ops) in reverse order; positions are `stride` floats apart
+__global__ void k_map_positions(const DevOp* __restrict__ ops, int n_ops, float* __restrict__ pos, uint32_t stride, uint8_t* __restrict__ empty_mask, uint32_t n) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float* q = pos + (size_t)i * stride;
+	V3 pw = v3(q[0], q[1], q[2]);
+	bool empty = false;
+	for (int o = n_ops - 1; o >= 0; --o) {
+		const DevOp& op = ops[o];
+		if (op.type == 0) {
+			if (op.n_tets == 0) continue;
+			bool in_deformed = false;
+			if (box_contains(op.wbmin, op.wbmax, pw)) {
+				V3 p = unwarp_position(pw, op.amin, op.amax);
+				float b[4];
+				int t = find_tet(op, p, b);
+				if (t >= 0) {
+					uint4 tv = __ldg(reinterpret_cast<const uint4*>(op.tets) + t);
+					pw = warp_position(bary_mix(b, ldv(op.orig_verts, tv.x), ldv(op.orig_verts, tv.y), ldv(op.orig_verts, tv.z), ldv(op.orig_verts, tv.w)), op.amin, op.amax);
+					in_deformed = true;
+				}
+			}
+			if (!in_deformed && box_contains(op.owbmin, op.owbmax, pw)) {
+				V3 p = unwarp_position(pw, op.amin, op.amax);
+				int level = mip_from_pos(p);
+				if (bitfield_at(cascaded_grid_idx_at(p, (uint32_t)level), (uint32_t)level, op.obits)) empty = true;
+			}
+		} else {
+			V3 dw = v3(0.5f, 0.5f, 0.5f);
+			DevOp tmp_free = op;  // translate_in_box_pos never touches a direction
+			tmp_free.correct_dir = 0;
+			affine_map(tmp_free, pw, dw, empty);
+		}
+	}
+	q[0] = pw.x; q[1] = pw.y; q[2] = pw.z;
+	if (empty && empty_mask) empty_mask[i] = 1;
+}
+
+// EditOperator::compute_poisson_residual_density (compute_poisson_residual_density_kernel, cage_deformation.cu:341-383):
+// density_network_output[i] += (half) interpolated residual density, for the first tet that contains the (warped) position
+__global__ void k_poisson_residual_density(const DevOp* __restrict__ ops, int n_ops, const float* __restrict__ pos, uint32_t stride, __half* __restrict__ density_out, uint32_t n) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* q = pos + (size_t)i * stride;
+	const V3 pw = v3(q[0], q[1], q[2]);
+	for (int o = n_ops - 1; o >= 0; --o) {
+		const DevOp& op = ops[o];
+		if (op.type != 0 || !op.apply_poisson || !op.has_poisson_data || op.n_tets == 0) continue;
+		V3 p = unwarp_position(pw, op.amin, op.amax);
+		if (!box_contains(op.bmin, op.bmax, p)) continue;
+		float b[4];
+		int t = find_tet(op, p, b);
+		if (t < 0) continue;
+		uint4 tv = __ldg(reinterpret_cast<const uint4*>(op.tets) + t);
+		float res = bary_mix1(b, __ldg(op.rd + tv.x), __ldg(op.rd + tv.y), __ldg(op.rd + tv.z), __ldg(op.rd + tv.w));
+		density_out[i] = __hadd(density_out[i], __float2half_rn(res));
+	}
 }
 
 __global__ void k_march_trace(const DevFrame f, const uint8_t* __restrict__ bitfield, const uint32_t* __restrict__ pixels, uint32_t n_pixels,
@@ -604,6 +668,7 @@ struct GridUpdateArgs {
 	float amin[3], amax[3];
 	int density_activation, apply_ops;
 };
+template <bool ACC16>
 __global__ void __launch_bounds__(128) k_density_grid_update(const DevModel m, const DevOp* __restrict__ ops, int n_ops, const GridUpdateArgs a,
                                                              const float* __restrict__ grid, float* __restrict__ grid_tmp) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -654,7 +719,7 @@ __global__ void __launch_bounds__(128) k_density_grid_update(const DevModel m, c
 		}
 		uint32_t dens[8], rgbo[8];
 		encode_to_a32(S.a32, m, valid, pw, tid);
-		tc::run_network(tc::single_tile_ctx(S, tmem_base), phase, dw, true, dens, rgbo);
+		tc::run_network<ACC16>(tc::single_tile_ctx(S, tmem_base), phase, dw, true, dens, rgbo);
 		if (valid) {
 			__half h = __float2half_rn(network_to_density(__half2float(__ushort_as_half((unsigned short)(dens[0] & 0xffffu))), a.density_activation));
 			if (a.apply_ops) {
@@ -858,6 +923,7 @@ struct NsbContext {
 	unsigned long long* d_stats = nullptr;
 	RayRec* d_list = nullptr;
 	size_t list_capacity = 0;
+	int acc16 = 0;                 // MLP accumulator policy: 0 fp32 TMEM accumulators, 1 fp16 (nsb_set_mlp_accumulator)
 	int use_ws = 0;                // NSB_WS=1: frames without operators go through the warp-specialised kernel (experimental; default k_render_fused<false>)
 	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
 	int dda_budget = DDA_BUDGET;
@@ -946,33 +1012,39 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	// k_render_fused: ONE CTA of NSB_TILES tiles per SM (512 threads x 128 registers = the whole register file; TMEM 64 columns
 	// per tile; shared memory 20 KB weights + 23 KB per tile).
 	c->ctas_per_sm = 1;
-	CU(set_smem((const void*)k_render_fused<false>, sizeof(RenderSmem), 1));
-	CU(set_smem((const void*)k_render_fused<true>, sizeof(RenderSmem), 1));
+	CU(set_smem((const void*)k_render_fused<false, false>, sizeof(RenderSmem), 1));
+	CU(set_smem((const void*)k_render_fused<true, false>, sizeof(RenderSmem), 1));
+	CU(set_smem((const void*)k_render_fused<false, true>, sizeof(RenderSmem), 1));
+	CU(set_smem((const void*)k_render_fused<true, true>, sizeof(RenderSmem), 1));
 	cudaFuncAttributes fa;
-	CU(cudaFuncGetAttributes(&fa, k_render_fused<false>));
+	CU(cudaFuncGetAttributes(&fa, k_render_fused<false, false>));
 	const int by_smem_tile = (int)(prop.sharedMemPerMultiprocessor / (sizeof(tc::TileSmem) + 1024));
 	{   // the operator-level kernels: one tile per CTA, residency from registers / shared memory
 		cudaFuncAttributes fi;
-		CU(cudaFuncGetAttributes(&fi, k_inference<false>));
+		CU(cudaFuncGetAttributes(&fi, k_inference<false, false>));
 		int r = fi.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fi.numRegs * 128)) : 4;
 		c->inference_ctas_per_sm = r < by_smem_tile ? r : by_smem_tile;
 		if (c->inference_ctas_per_sm > 5) c->inference_ctas_per_sm = 5;
 		if (c->inference_ctas_per_sm < 1) c->inference_ctas_per_sm = 1;
-		CU(cudaFuncGetAttributes(&fi, k_density_grid_update));
+		CU(cudaFuncGetAttributes(&fi, k_density_grid_update<false>));
 		r = fi.numRegs > 0 ? (int)(prop.regsPerMultiprocessor / (fi.numRegs * 128)) : 4;
 		c->grid_update_ctas_per_sm = r < by_smem_tile ? r : by_smem_tile;
 		if (c->grid_update_ctas_per_sm > 5) c->grid_update_ctas_per_sm = 5;
 		if (c->grid_update_ctas_per_sm < 1) c->grid_update_ctas_per_sm = 1;
-		CU(set_smem((const void*)k_inference<false>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
-		CU(set_smem((const void*)k_inference<true>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
-		CU(set_smem((const void*)k_density_grid_update, sizeof(tc::TileSmem), c->grid_update_ctas_per_sm));
+		CU(set_smem((const void*)k_inference<false, false>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
+		CU(set_smem((const void*)k_inference<true, false>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
+		CU(set_smem((const void*)k_inference<false, true>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
+		CU(set_smem((const void*)k_inference<true, true>, sizeof(tc::TileSmem), c->inference_ctas_per_sm));
+		CU(set_smem((const void*)k_density_grid_update<false>, sizeof(tc::TileSmem), c->grid_update_ctas_per_sm));
+		CU(set_smem((const void*)k_density_grid_update<true>, sizeof(tc::TileSmem), c->grid_update_ctas_per_sm));
 	}
 	if (const char* e = getenv("NSB_CARVEOUT")) {  // experiments
-		CU(cudaFuncSetAttribute(k_render_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-		CU(cudaFuncSetAttribute(k_render_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+		CU(cudaFuncSetAttribute(k_render_fused<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+		CU(cudaFuncSetAttribute(k_render_fused<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
 	}
 	CU(set_smem((const void*)k_render_ws, sizeof(ws::Smem), 1));
 	if (const char* e = getenv("NSB_WS")) c->use_ws = atoi(e) != 0;
+	if (const char* e = getenv("NSB_MLP_ACC16")) c->acc16 = atoi(e) != 0;
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
 	if (const char* e = getenv("NSB_CHUNK")) { int v = atoi(e); if (v >= 0 && v <= 65535) c->refill_thr |= v << 8; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
@@ -1023,7 +1095,8 @@ static void to_operand_layout(const uint16_t* W, uint32_t N, uint32_t K, uint8_t
 		}
 }
 
-extern "C" NsbStatus nsb_upload_model(NsbContext* c, const NsbModelDesc* desc, const uint16_t* params, uint64_t n_params) {
+// params_on_device: the block is read where tcnn::Trainer keeps it; only the 20 KB of MLP weights pass through the host (to be laid out as UMMA operands)
+static NsbStatus upload_model_impl(NsbContext* c, const NsbModelDesc* desc, const uint16_t* params, uint64_t n_params, bool params_on_device) {
 	if (!c || !desc || !params) return fail(NSB_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(c->device));
 	DevModel m{};
@@ -1035,7 +1108,12 @@ extern "C" NsbStatus nsb_upload_model(NsbContext* c, const NsbModelDesc* desc, c
 	c->d_grid = nullptr; c->d_wimage = nullptr; c->d_wrow = nullptr;
 	// block order: density MLP, rgb MLP, hash grid (nerf_network_full.h:316-349)
 	std::vector<uint8_t> image(tc::W_BYTES);
-	const uint16_t* w = params;
+	std::vector<uint16_t> mlp_host;
+	if (params_on_device) {
+		mlp_host.resize(kMlpParams);
+		CU(cudaMemcpy(mlp_host.data(), params, kMlpParams * 2, cudaMemcpyDeviceToHost));
+	}
+	const uint16_t* w = params_on_device ? mlp_host.data() : params;
 	to_operand_layout(w, 64, 32, image.data() + tc::W1_OFF); w += 64 * 32;
 	to_operand_layout(w, 16, 64, image.data() + tc::W2_OFF); w += 16 * 64;
 	to_operand_layout(w, 64, 32, image.data() + tc::W3_OFF); w += 64 * 32;
@@ -1044,9 +1122,9 @@ extern "C" NsbStatus nsb_upload_model(NsbContext* c, const NsbModelDesc* desc, c
 	CU(cudaMalloc(&c->d_wimage, tc::W_BYTES));
 	CU(cudaMemcpy(c->d_wimage, image.data(), tc::W_BYTES, cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&c->d_wrow, kMlpParams * 2));
-	CU(cudaMemcpy(c->d_wrow, params, kMlpParams * 2, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_wrow, params, kMlpParams * 2, params_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&c->d_grid, n_grid * 4));
-	CU(cudaMemcpy(c->d_grid, params + kMlpParams, n_grid * 4, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_grid, params + kMlpParams, n_grid * 4, params_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
 	m.grid = c->d_grid;
 	for (uint32_t l = 0; l < desc->n_levels; ++l) m.levels[l].base = c->d_grid + (uintptr_t)m.levels[l].base / sizeof(__half2);
 	m.w_image = c->d_wimage;
@@ -1062,16 +1140,25 @@ extern "C" NsbStatus nsb_upload_model(NsbContext* c, const NsbModelDesc* desc, c
 	return NSB_OK;
 }
 
-extern "C" NsbStatus nsb_upload_occupancy(NsbContext* c, const uint8_t* bitfield, uint64_t n_bytes) {
+extern "C" NsbStatus nsb_upload_model(NsbContext* c, const NsbModelDesc* desc, const uint16_t* params, uint64_t n_params) {
+	return upload_model_impl(c, desc, params, n_params, false);
+}
+extern "C" NsbStatus nsb_upload_model_dev(NsbContext* c, const NsbModelDesc* desc, const uint16_t* params_dev, uint64_t n_params) {
+	return upload_model_impl(c, desc, params_dev, n_params, true);
+}
+
+static NsbStatus upload_occupancy_impl(NsbContext* c, const uint8_t* bitfield, uint64_t n_bytes, bool on_device) {
 	if (!c || !bitfield) return fail(NSB_ERR_INVALID, "null argument");
 	if (n_bytes != NSB_BITFIELD_BYTES) return fail(NSB_ERR_INVALID, "bitfield must be %u bytes (5 x 128^3 / 8)", NSB_BITFIELD_BYTES);
 	CU(cudaSetDevice(c->device));
 	if (!c->d_bitfield) CU(cudaMalloc(&c->d_bitfield, NSB_BITFIELD_BYTES));
 	CU(cudaDeviceSynchronize());
-	CU(cudaMemcpy(c->d_bitfield, bitfield, NSB_BITFIELD_BYTES, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(c->d_bitfield, bitfield, NSB_BITFIELD_BYTES, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
 	c->has_occ = true;
 	return NSB_OK;
 }
+extern "C" NsbStatus nsb_upload_occupancy(NsbContext* c, const uint8_t* bitfield, uint64_t n_bytes) { return upload_occupancy_impl(c, bitfield, n_bytes, false); }
+extern "C" NsbStatus nsb_upload_occupancy_dev(NsbContext* c, const uint8_t* bitfield_dev, uint64_t n_bytes) { return upload_occupancy_impl(c, bitfield_dev, n_bytes, true); }
 
 static NsbStatus ensure_grid_buffers(NsbContext* c) {
 	const uint32_t n_blocks = (GRIDVOL + 256 * 64 - 1) / (256 * 64);
@@ -1137,7 +1224,7 @@ extern "C" NsbStatus nsb_update_density_grid(NsbContext* c, const NsbGridUpdate*
 		uint32_t grid = (n_total + 127u) / 128u;
 		uint32_t cap = (uint32_t)(c->sm_count * c->grid_update_ctas_per_sm);
 		if (grid > cap) grid = cap;
-		k_density_grid_update<<<grid, 128, sizeof(tc::TileSmem), st>>>(c->model, c->d_ops, c->n_ops, a, c->d_density_grid, c->d_density_tmp);
+		(c->acc16 ? k_density_grid_update<true> : k_density_grid_update<false>)<<<grid, 128, sizeof(tc::TileSmem), st>>>(c->model, c->d_ops, c->n_ops, a, c->d_density_grid, c->d_density_tmp);
 	}
 	k_ema_grid<<<(NSB_GRID_CELLS + 255) / 256, 256, 0, st>>>((uint32_t)NSB_GRID_CELLS, u->decay, c->d_density_grid, c->d_density_tmp);  // :3634
 	CU(cudaGetLastError());
@@ -1393,7 +1480,7 @@ extern "C" NsbStatus nsb_poisson_boundary(NsbContext* c, const float* points, ui
 	CUB_(cudaMemcpy(d_aabb, aabb, sizeof(aabb), cudaMemcpyHostToDevice));
 	uint32_t grid = n_padded / 128, cap = (uint32_t)(c->sm_count * c->inference_ctas_per_sm);
 	if (grid > cap) grid = cap;
-	k_inference<false><<<grid, 128, sizeof(tc::TileSmem)>>>(c->model, d_coords, n, d_net, n_padded);  // inference_mixed_precision (:2286)
+	(c->acc16 ? k_inference<false, true> : k_inference<false, false>)<<<grid, 128, sizeof(tc::TileSmem)>>>(c->model, d_coords, n, d_net, n_padded);  // inference_mixed_precision (:2286)
 	const float scale = (float)(4 * M_PI / (double)n_sh);                                                // :2341
 	nsb::rebuild::k_boundary_fit<<<n_points, 32>>>(d_net, n_padded, d_coords, n_sh, p->rgb_activation, p->density_activation,
 	                                               p->is_inside ? c->d_bitfield : nullptr, d_aabb, scale, d_dens, d_shs);
@@ -1543,6 +1630,7 @@ static NsbStatus to_dev_frame(const NsbFrame* f, DevFrame* d) {
 	host_pixel_offset(f->snap_to_pixel_centers ? 0u : f->spp_index, d->pix_off);
 	d->apply_ops = f->apply_operators; d->poisson_target = f->poisson_target; d->linear_colors = f->linear_colors;
 	d->min_mip = f->min_mip < 0 ? 0 : (f->min_mip > 4 ? 4 : f->min_mip);
+	d->show_accel = f->show_accel != 0;
 	d->tile_rank = f->tile_rank; d->tile_world = f->tile_world;
 	d->tiles_x = (f->width + TILE_W - 1) / TILE_W;
 	d->tiles_y = (f->height + TILE_H - 1) / TILE_H;
@@ -1579,13 +1667,13 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
 		if (grid > (my_tiles + NSB_TILES - 1) / NSB_TILES) grid = (uint32_t)((my_tiles + NSB_TILES - 1) / NSB_TILES);
 		const bool ops_on = f.apply_ops && c->n_ops > 0;
-		if (!ops_on && c->use_ws && (uint64_t)f.W * (uint64_t)f.H < (1ull << 28)) {  // k_render_ws ships the pixel in 28 bits of a flag word
+		if (!ops_on && c->use_ws && !c->acc16 && !f.show_accel && (uint64_t)f.W * (uint64_t)f.H < (1ull << 28)) {  // k_render_ws ships the pixel in 28 bits of a flag word
 			uint32_t g2 = (uint32_t)c->sm_count;
 			if (g2 > (my_tiles + ws::PT - 1) / ws::PT) g2 = (uint32_t)((my_tiles + ws::PT - 1) / ws::PT);
 			k_render_ws<<<g2, ws::THREADS, sizeof(ws::Smem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list,
 			                                                           c->d_counters, c->d_counters + 1, c->d_stats, c->refill_thr, c->dda_budget);
 		} else {
-		auto kernel = ops_on ? k_render_fused<true> : k_render_fused<false>;
+		auto kernel = ops_on ? (c->acc16 ? k_render_fused<true, true> : k_render_fused<true, false>) : (c->acc16 ? k_render_fused<false, true> : k_render_fused<false, false>);
 		kernel<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
 		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
 		                                                          c->refill_thr, c->dda_budget);
@@ -1617,6 +1705,13 @@ extern "C" NsbStatus nsb_render_host(NsbContext* c, const NsbFrame* frame, float
 	CU(cudaMemcpyAsync(fb_host, c->d_fb, n * 16, cudaMemcpyDeviceToHost, c->stream));
 	if (depth_host) CU(cudaMemcpyAsync(depth_host, c->d_depth, n * 4, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_set_mlp_accumulator(NsbContext* c, int32_t policy) {
+	if (!c) return fail(NSB_ERR_INVALID, "null context");
+	if (policy != NSB_MLP_ACC_F32 && policy != NSB_MLP_ACC_F16) return fail(NSB_ERR_INVALID, "unknown accumulator policy %d", policy);
+	c->acc16 = policy == NSB_MLP_ACC_F16;
 	return NSB_OK;
 }
 
@@ -1722,7 +1817,7 @@ static NsbStatus inference_impl(NsbContext* c, const float* coords, uint32_t n, 
 	uint32_t grid = n_padded / 128;
 	uint32_t cap = (uint32_t)(c->sm_count * c->inference_ctas_per_sm);
 	if (grid > cap) grid = cap;
-	k_inference<DENSITY_ONLY><<<grid, 128, sizeof(tc::TileSmem), (cudaStream_t)stream>>>(c->model, coords, n, reinterpret_cast<__half*>(out), n_padded);
+	(c->acc16 ? k_inference<DENSITY_ONLY, true> : k_inference<DENSITY_ONLY, false>)<<<grid, 128, sizeof(tc::TileSmem), (cudaStream_t)stream>>>(c->model, coords, n, reinterpret_cast<__half*>(out), n_padded);
 	CU(cudaGetLastError());
 	return NSB_OK;
 }
@@ -1742,21 +1837,69 @@ extern "C" NsbStatus nsb_encode(NsbContext* c, const float* coords, uint32_t n, 
 	CU(cudaGetLastError());
 	return NSB_OK;
 }
-extern "C" NsbStatus nsb_map_rays(NsbContext* c, float* coords, uint8_t* empty_mask, uint32_t n, void* stream) {
+// op_index < 0: every uploaded operator in reverse list order (the loops of testbed_nerf.cu:2868-2904, outputs cleared first like :2863-2866, :2898);
+// op_index >= 0: that operator alone = one EditOperator virtual call (outputs are not cleared, as the virtuals do not clear them)
+static NsbStatus op_range(NsbContext* c, int32_t op_index, const DevOp** ops, int* n_ops) {
+	if (op_index >= c->n_ops) return fail(NSB_ERR_INVALID, "operator %d of %d", op_index, c->n_ops);
+	*ops = op_index < 0 ? c->d_ops : c->d_ops + op_index;
+	*n_ops = op_index < 0 ? c->n_ops : 1;
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_map_rays_op(NsbContext* c, int32_t op_index, float* coords, uint8_t* empty_mask, uint32_t n, void* stream) {
 	if (!c || !coords || !empty_mask) return fail(NSB_ERR_INVALID, "null argument");
 	if (n == 0) return NSB_OK;
 	CU(cudaSetDevice(c->device));
-	CU(cudaMemsetAsync(empty_mask, 0, n, (cudaStream_t)stream));  // :2898
+	if (op_index < 0) CU(cudaMemsetAsync(empty_mask, 0, n, (cudaStream_t)stream));  // :2898
 	if (c->n_ops == 0) return NSB_OK;
-	k_map_rays<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c->d_ops, c->n_ops, coords, empty_mask, n);
+	const DevOp* ops; int n_ops;
+	NsbStatus st = op_range(c, op_index, &ops, &n_ops);
+	if (st != NSB_OK) return st;
+	k_map_rays<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ops, n_ops, coords, empty_mask, n);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_map_rays(NsbContext* c, float* coords, uint8_t* empty_mask, uint32_t n, void* stream) { return nsb_map_rays_op(c, -1, coords, empty_mask, n, stream); }
+extern "C" NsbStatus nsb_poisson_residuals_op(NsbContext* c, int32_t op_index, const float* coords, uint32_t n, float* sh, float* od, float* rd, void* stream) {
+	if (!c || !coords || !sh || !od || !rd) return fail(NSB_ERR_INVALID, "null argument");
+	if (n == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	if (op_index < 0) {  // :2863-2866
+		CU(cudaMemsetAsync(sh, 0, (size_t)n * 27 * sizeof(float), (cudaStream_t)stream));
+		CU(cudaMemsetAsync(od, 0, (size_t)n * sizeof(float), (cudaStream_t)stream));
+		CU(cudaMemsetAsync(rd, 0, (size_t)n * sizeof(float), (cudaStream_t)stream));
+	}
+	if (c->n_ops == 0) return NSB_OK;
+	const DevOp* ops; int n_ops;
+	NsbStatus st = op_range(c, op_index, &ops, &n_ops);
+	if (st != NSB_OK) return st;
+	k_poisson<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ops, n_ops, coords, n, sh, od, rd);
 	CU(cudaGetLastError());
 	return NSB_OK;
 }
 extern "C" NsbStatus nsb_poisson_residuals(NsbContext* c, const float* coords, uint32_t n, float* sh, float* od, float* rd, void* stream) {
-	if (!c || !coords || !sh || !od || !rd) return fail(NSB_ERR_INVALID, "null argument");
+	return nsb_poisson_residuals_op(c, -1, coords, n, sh, od, rd, stream);
+}
+extern "C" NsbStatus nsb_map_positions(NsbContext* c, int32_t op_index, float* positions, uint32_t stride_floats, uint8_t* empty_mask, uint32_t n, void* stream) {
+	if (!c || !positions || stride_floats < 3) return fail(NSB_ERR_INVALID, "bad arguments");
 	if (n == 0) return NSB_OK;
 	CU(cudaSetDevice(c->device));
-	k_poisson<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c->d_ops, c->n_ops, coords, n, sh, od, rd);
+	if (op_index < 0 && empty_mask) CU(cudaMemsetAsync(empty_mask, 0, n, (cudaStream_t)stream));  // :3595
+	if (c->n_ops == 0) return NSB_OK;
+	const DevOp* ops; int n_ops;
+	NsbStatus st = op_range(c, op_index, &ops, &n_ops);
+	if (st != NSB_OK) return st;
+	k_map_positions<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ops, n_ops, positions, stride_floats, empty_mask, n);
+	CU(cudaGetLastError());
+	return NSB_OK;
+}
+extern "C" NsbStatus nsb_poisson_residual_density(NsbContext* c, int32_t op_index, const float* positions, uint32_t stride_floats, uint16_t* density_fp16, uint32_t n, void* stream) {
+	if (!c || !positions || !density_fp16 || stride_floats < 3) return fail(NSB_ERR_INVALID, "bad arguments");
+	if (n == 0 || c->n_ops == 0) return NSB_OK;
+	CU(cudaSetDevice(c->device));
+	const DevOp* ops; int n_ops;
+	NsbStatus st = op_range(c, op_index, &ops, &n_ops);
+	if (st != NSB_OK) return st;
+	k_poisson_residual_density<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ops, n_ops, positions, stride_floats, reinterpret_cast<__half*>(density_fp16), n);
 	CU(cudaGetLastError());
 	return NSB_OK;
 }

@@ -157,7 +157,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 // cute::UMMA::InstrDescriptor for kind::f16: D=F32 (c_format 1 @ [4,6)), A=B=F16 (0), both K-major (0),
 // N>>3 @ [17,23), M>>4 @ [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+// acc16: D=F16 (c_format 0) — the accumulator is rounded to fp16 by every K=16 instruction, the arithmetic of wmma m16n16k16 with __half
+// accumulator fragments (tiny-cuda-nn's FullyFusedMLP of the reference's era); each fp16 still occupies one 32-bit TMEM column (low half).
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, bool acc16 = false) { return (acc16 ? 0u : (1u << 4)) | ((N >> 3) << 17) | ((M >> 4) << 24); }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
 	asm volatile(
@@ -173,9 +175,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // One layer: D[128 x N] = A[128 x K] * W[N x K]^T, issued by ONE thread; completion arrives on mma_bar.
-template <uint32_t N, uint32_t K>
+template <uint32_t N, uint32_t K, bool ACC16 = false>
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
-	constexpr uint32_t idesc = make_idesc(ROWS, N);
+	constexpr uint32_t idesc = make_idesc(ROWS, N, ACC16);
 #pragma unroll
 	for (uint32_t k = 0; k < K / 16; ++k) {
 		// one instruction consumes K=16 = two 8-wide k-chunks; chunk stride = rows*16 bytes
@@ -189,12 +191,12 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, ui
 // The MMA is issued by lane 0 of warp 0, but the WHOLE warp takes the branch and re-converges before anybody
 // waits on the mbarrier: if lanes 1-31 reached mbarrier.try_wait first (divergent from lane 0), the warp would
 // sleep in the hardware wait until its time-out before lane 0 ever issued the instruction it is waiting for.
-template <uint32_t N, uint32_t K>
+template <uint32_t N, uint32_t K, bool ACC16 = false>
 __device__ __forceinline__ void issue_converged(uint32_t row, uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
 	if (row < 32) {  // warp 0 of the tile
 		if (row == 0) {
 			tc_fence_after();
-			issue_layer<N, K>(tmem_d, a_addr, w_addr, bar);
+			issue_layer<N, K, ACC16>(tmem_d, a_addr, w_addr, bar);
 		}
 		__syncwarp();
 	}
@@ -268,8 +270,17 @@ __device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits) 
 __device__ __forceinline__ uint32_t pack(uint32_t a_bits, uint32_t b_bits) {
 	return pack_h2(__floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits)));
 }
+// two TMEM columns -> packed half2: fp32 accumulators are rounded here, fp16 accumulators (low half of each column) are just gathered
+template <bool ACC16> __device__ __forceinline__ uint32_t pack_acc(uint32_t a_bits, uint32_t b_bits) {
+	return ACC16 ? __byte_perm(a_bits, b_bits, 0x5410) : pack(a_bits, b_bits);
+}
+template <bool ACC16> __device__ __forceinline__ uint32_t relu_pack_acc(uint32_t a_bits, uint32_t b_bits) {
+	uint32_t p = pack_acc<ACC16>(a_bits, b_bits);
+	return pack_h2(__hmax2(*reinterpret_cast<__half2*>(&p), __floats2half2_rn(0.0f, 0.0f)));
+}
 
 // Epilogue of a 64-wide hidden layer: TMEM fp32 [row][0..63] -> ReLU -> fp16 -> a64 row (8 chunks)
+template <bool ACC16 = false>
 __device__ __forceinline__ void epilogue_hidden(uint8_t* a64, uint32_t tmem_row, uint32_t row) {
 #pragma unroll
 	for (uint32_t q = 0; q < 2; ++q) {
@@ -279,8 +290,8 @@ __device__ __forceinline__ void epilogue_hidden(uint8_t* a64, uint32_t tmem_row,
 		tmem_wait_ld();
 #pragma unroll
 		for (uint32_t j = 0; j < 4; ++j) {
-			uint4 c = make_uint4(relu_pack(r[8 * j + 0], r[8 * j + 1]), relu_pack(r[8 * j + 2], r[8 * j + 3]), relu_pack(r[8 * j + 4], r[8 * j + 5]),
-			                     relu_pack(r[8 * j + 6], r[8 * j + 7]));
+			uint4 c = make_uint4(relu_pack_acc<ACC16>(r[8 * j + 0], r[8 * j + 1]), relu_pack_acc<ACC16>(r[8 * j + 2], r[8 * j + 3]), relu_pack_acc<ACC16>(r[8 * j + 4], r[8 * j + 5]),
+			                     relu_pack_acc<ACC16>(r[8 * j + 6], r[8 * j + 7]));
 			store_chunk(a64, 4 * q + j, row, c);
 		}
 	}
@@ -293,6 +304,7 @@ __device__ __forceinline__ void epilogue_hidden(uint8_t* a64, uint32_t tmem_row,
 // `phase` is the running parity of the tile's mma_bar (one flip per layer).
 // `a_first`: shared-window address of the first layer's operand when it does not live in c.a32 (the warp-specialised renderer's producers
 // write the grid features into their own double-buffered operand); 0 = c.a32.
+template <bool ACC16 = false>
 __device__ __forceinline__ void run_network(const TileCtx& c, uint32_t& phase, V3 dw, bool density_only, uint32_t* dens, uint32_t* rgb, uint32_t a_first = 0) {
 	const uint32_t row = c.row;
 	const uint32_t tmem_row = c.tmem + ((row & ~31u) << 16);  // lane field = first lane of this warp's quarter
@@ -302,19 +314,19 @@ __device__ __forceinline__ void run_network(const TileCtx& c, uint32_t& phase, V
 	fence_async_smem();                                                 \
 	tc_fence_before();                                                  \
 	tile_sync(c);                                                       \
-	issue_converged<N_, K_>(row, c.tmem, A_, w + W_, c.mma_bar);        \
+	issue_converged<N_, K_, ACC16>(row, c.tmem, A_, w + W_, c.mma_bar); \
 	mbar_wait(c.mma_bar, phase); phase ^= 1;                            \
 	tc_fence_after();
 
 	NSB_SYNC_ISSUE(64, 32, a_first, W1_OFF)   // L1: grid features (32) -> 64
-	epilogue_hidden(c.a64, tmem_row, row);
+	epilogue_hidden<ACC16>(c.a64, tmem_row, row);
 	NSB_SYNC_ISSUE(16, 64, a64, W2_OFF)   // L2: a64 (64) -> 16
 	{
 		uint32_t r[16];
 		tmem_ld16(tmem_row, r);
 		tmem_wait_ld();
 #pragma unroll
-		for (int i = 0; i < 8; ++i) dens[i] = pack(r[2 * i], r[2 * i + 1]);
+		for (int i = 0; i < 8; ++i) dens[i] = pack_acc<ACC16>(r[2 * i], r[2 * i + 1]);
 	}
 	if (density_only) { tc_fence_before(); return; }
 	// rgb-network input: rows 0-15 = density MLP output, 16-31 = SH (nerf_network_full.h:52,67,79)
@@ -325,16 +337,16 @@ __device__ __forceinline__ void run_network(const TileCtx& c, uint32_t& phase, V
 	store_chunk(c.a32, 2, row, make_uint4(pack_h2(sh[0]), pack_h2(sh[1]), pack_h2(sh[2]), pack_h2(sh[3])));
 	store_chunk(c.a32, 3, row, make_uint4(pack_h2(sh[4]), pack_h2(sh[5]), pack_h2(sh[6]), pack_h2(sh[7])));
 	NSB_SYNC_ISSUE(64, 32, a32, W3_OFF)   // L3: a32 -> 64
-	epilogue_hidden(c.a64, tmem_row, row);
+	epilogue_hidden<ACC16>(c.a64, tmem_row, row);
 	NSB_SYNC_ISSUE(64, 64, a64, W4_OFF)   // L4: a64 -> 64
-	epilogue_hidden(c.a64, tmem_row, row);
+	epilogue_hidden<ACC16>(c.a64, tmem_row, row);
 	NSB_SYNC_ISSUE(16, 64, a64, W5_OFF)   // L5: a64 -> 16
 	{
 		uint32_t r[16];
 		tmem_ld16(tmem_row, r);
 		tmem_wait_ld();
 #pragma unroll
-		for (int i = 0; i < 8; ++i) rgb[i] = pack(r[2 * i], r[2 * i + 1]);
+		for (int i = 0; i < 8; ++i) rgb[i] = pack_acc<ACC16>(r[2 * i], r[2 * i + 1]);
 	}
 	tc_fence_before();
 #undef NSB_SYNC_ISSUE

@@ -3,7 +3,9 @@
 // it calls the stock code. Header-only; Eigen-free (cameras are passed as 12 floats, column-major like Eigen's storage).
 //
 //   ngp_b200::NerfNetwork      <- NerfNetwork<T>            (nerf_network.h:87-120): inference_mixed_precision, density
-//   ngp_b200::EditOperator     <- EditOperator              (editing/edit_operator.h:25-94): the POD handed to the tracer
+//   ngp_b200::EditOperator     <- EditOperator              (editing/edit_operator.h:25-94): the POD handed to the tracer + the four device
+//                                                            virtuals (map_rays, map_positions, compute_poisson_full_residuals,
+//                                                            compute_poisson_residual_density) once the operator is attached to a tracer
 //   ngp_b200::NerfTracer       <- Testbed::NerfTracer       (testbed.h:129-240): operator list management, trace == render
 //   ngp_b200::render_nerf(...) <- Testbed::render_nerf      (testbed.h:305, testbed_nerf.cu:3066)
 //
@@ -42,6 +44,10 @@ class NerfNetwork {
 public:
 	NerfNetwork(std::shared_ptr<Context> ctx, const NsbModelDesc& desc) : m_ctx(std::move(ctx)), m_desc(desc) {}
 	void set_params(const uint16_t* params_fp16, uint64_t n_params) { check(nsb_upload_model(m_ctx->get(), &m_desc, params_fp16, n_params), "nsb_upload_model"); }
+	// the block where tcnn::Trainer keeps it (device memory): no 26 MB round trip through the host
+	void set_params_device(const uint16_t* params_fp16_dev, uint64_t n_params) { check(nsb_upload_model_dev(m_ctx->get(), &m_desc, params_fp16_dev, n_params), "nsb_upload_model_dev"); }
+	// tcnn's FullyFusedMLP accumulates in __half fragments; NSB_MLP_ACC_F32 (default) accumulates wide (see include/nerfshop_b200.h)
+	void set_accumulator(NsbMlpAccumulator policy) { check(nsb_set_mlp_accumulator(m_ctx->get(), policy), "nsb_set_mlp_accumulator"); }
 	uint64_t n_params() const { uint64_t n = 0; check(nsb_model_n_params(&m_desc, &n), "nsb_model_n_params"); return n; }
 	uint32_t padded_output_width() const { return 16; }          // nerf_network.h: rgb MLP output padded to 16
 	uint32_t padded_density_output_width() const { return 16; }
@@ -60,10 +66,35 @@ private:
 };
 
 // An operator is the POD of its kernel arguments; the interactive tooling that produces it (GrowingSelection, TetGen, ...)
-// stays in the host application. CageDeformation / AffineDuplication fill the respective half of NsbEditOp.
+// stays in the host application. CageDeformation / AffineDuplication fill the respective half of NsbEditOp. Once added to a
+// NerfTracer the operator knows its slot in the uploaded list and the device virtuals of the reference's EditOperator work
+// (edit_operator.h:43,45,68,81; PitchedPtr arguments become pointer + stride, GPUMatrixDynamic<bool> a byte array).
 struct EditOperator {
 	NsbEditOp pod{};
 	virtual ~EditOperator() = default;
+	// nerf_coords: NerfCoordinate per sample (7 floats); empty_mask is only ever set, like interpolate_tet / translate_in_box
+	virtual void map_rays(void* stream, float* nerf_coords_dev, uint8_t* empty_mask_dev, uint32_t n_elements) const {
+		check(nsb_map_rays_op(ctx(), m_index, nerf_coords_dev, empty_mask_dev, n_elements, stream), "nsb_map_rays_op");
+	}
+	virtual void map_positions(void* stream, float* nerf_pos_dev, uint32_t stride_floats, uint8_t* empty_mask_dev, uint32_t n_elements) const {
+		check(nsb_map_positions(ctx(), m_index, nerf_pos_dev, stride_floats, empty_mask_dev, n_elements, stream), "nsb_map_positions");
+	}
+	virtual void compute_poisson_full_residuals(void* stream, uint32_t n_elements, const float* network_input_dev, float* sh_boundary_dev, float* out_density_boundary_dev,
+	                                            float* residual_density_boundary_dev) const {
+		check(nsb_poisson_residuals_op(ctx(), m_index, network_input_dev, n_elements, sh_boundary_dev, out_density_boundary_dev, residual_density_boundary_dev, stream), "nsb_poisson_residuals_op");
+	}
+	virtual void compute_poisson_residual_density(void* stream, uint32_t n_elements, const float* input_position_dev, uint32_t stride_floats, uint16_t* density_network_output_dev) const {
+		check(nsb_poisson_residual_density(ctx(), m_index, input_position_dev, stride_floats, density_network_output_dev, n_elements, stream), "nsb_poisson_residual_density");
+	}
+
+private:
+	friend class NerfTracer;
+	NsbContext* ctx() const {
+		if (!m_ctx || m_index < 0) throw std::runtime_error("EditOperator: not attached to a NerfTracer (add_edit_operator first)");
+		return m_ctx;
+	}
+	NsbContext* m_ctx = nullptr;
+	int32_t m_index = -1;
 };
 struct CageDeformation : EditOperator {
 	CageDeformation() { pod.type = NSB_OP_CAGE; pod.residual_amplitude = 1.0f; }
@@ -82,13 +113,14 @@ public:
 	const std::vector<std::shared_ptr<EditOperator>>& edit_operators() const { return m_edit_operators; }
 	bool m_poisson_target = false;
 
-	// init_rays_from_camera + trace + shade in one call; returns n_hit like NerfTracer::trace.
-	uint32_t trace(const NsbFrame& frame, float* frame_buffer_dev, float* depth_buffer_dev, void* stream) {
+	// init_rays_from_camera + trace + shade in one call. Like NerfTracer::trace (:2998-3000) it synchronises the stream and returns n_hit;
+	// synchronise = false keeps the frame asynchronous (returns 0; n_hit is in stats() later).
+	uint32_t trace(const NsbFrame& frame, float* frame_buffer_dev, float* depth_buffer_dev, void* stream, bool synchronise = true) {
 		NsbFrame f = frame;
 		f.poisson_target = m_poisson_target ? 1 : 0;
 		check(nsb_render(m_ctx->get(), &f, frame_buffer_dev, depth_buffer_dev, stream), "nsb_render");
 		m_rendered = true;
-		return 0;  // asynchronous: n_hit is available from stats() (the reference synchronises here, :2998-3000)
+		return synchronise ? (uint32_t)stats().n_hit : 0u;
 	}
 	// ---- per-edit work kept on the device ----
 	// GrowingSelection::update_tet_mesh for operator i after a gizmo drag (growing_selection.cu:1615): no re-upload.
@@ -106,7 +138,11 @@ public:
 private:
 	void upload() {
 		std::vector<NsbEditOp> pods;
-		for (auto& op : m_edit_operators) pods.push_back(op->pod);
+		for (size_t i = 0; i < m_edit_operators.size(); ++i) {
+			m_edit_operators[i]->m_ctx = m_ctx->get();
+			m_edit_operators[i]->m_index = (int32_t)i;
+			pods.push_back(m_edit_operators[i]->pod);
+		}
 		check(nsb_set_edit_ops(m_ctx->get(), pods.empty() ? nullptr : pods.data(), (int32_t)pods.size()), "nsb_set_edit_ops");
 	}
 	std::shared_ptr<Context> m_ctx;
@@ -115,10 +151,10 @@ private:
 };
 
 // Testbed::render_nerf: the caller fills NsbFrame from the Testbed members listed at testbed_nerf.cu:3082-3138.
-inline void render_nerf(NerfTracer& tracer, const NsbFrame& frame, float* frame_buffer_dev, float* depth_buffer_dev, bool apply_operators, void* stream) {
+inline uint32_t render_nerf(NerfTracer& tracer, const NsbFrame& frame, float* frame_buffer_dev, float* depth_buffer_dev, bool apply_operators, void* stream, bool synchronise = false) {
 	NsbFrame f = frame;
 	f.apply_operators = apply_operators ? 1 : 0;
-	tracer.trace(f, frame_buffer_dev, depth_buffer_dev, stream);
+	return tracer.trace(f, frame_buffer_dev, depth_buffer_dev, stream, synchronise);
 }
 
 }  // namespace ngp_b200

@@ -51,6 +51,10 @@ class NerfRenderer:
         p = np.ascontiguousarray(params_u16, dtype=np.uint16)
         abi.check(self.lib, self.lib.nsb_upload_model(self.ctx, C.byref(desc), p.ctypes.data, p.size), "nsb_upload_model")
 
+    def set_mlp_accumulator(self, policy: int):
+        """NSB_MLP_ACC_F32 (default) or NSB_MLP_ACC_F16 (the arithmetic of tiny-cuda-nn's wmma __half accumulator fragments)."""
+        abi.check(self.lib, self.lib.nsb_set_mlp_accumulator(self.ctx, int(policy)), "nsb_set_mlp_accumulator")
+
     def upload_occupancy(self, bitfield: np.ndarray):
         b = np.ascontiguousarray(bitfield, dtype=np.uint8)
         abi.check(self.lib, self.lib.nsb_upload_occupancy(self.ctx, b.ctypes.data, b.size), "nsb_upload_occupancy")

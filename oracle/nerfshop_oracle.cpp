@@ -433,14 +433,32 @@ void encode_sh4(V3 dw, uint16_t* out /*16*/) {
 	for (int i = 0; i < 16; ++i) out[i] = f2h(o[i]);
 }
 
-// One fully-fused layer: y = W x, W [n_out x n_in] fp16 row-major, x fp16, accumulate wide, y -> fp16.
+// Accumulator policy of the fully fused MLPs (orc_set_mlp_policy):
+//   0 (default) wide: every output is the exactly-rounded dot product (double accumulate, one rounding to fp16) — what the CUDA path's
+//     tcgen05 kind::f16 MMAs with fp32 TMEM accumulators approximate to 2-4 fp16 ulps;
+//   1 half accumulator fragments: tiny-cuda-nn's FullyFusedMLP of that era runs wmma m16n16k16 with __half accumulators (SURVEY.md
+//     Appendix B, unverifiable here): the running sum is rounded to fp16 after every k-chunk of 16 (products and the 16-term partial
+//     sum inside one MMA are kept wide). Used to MEASURE how far the two policies are apart in the framebuffer (tests/test_mlp_policy.py).
+int g_mlp_policy = 0;
+
+// One fully-fused layer: y = W x, W [n_out x n_in] fp16 row-major, x fp16, y -> fp16.
 void mlp_layer(const float* W, int n_out, int n_in, const uint16_t* x, bool relu, uint16_t* y) {
 	double xf[64];
 	for (int k = 0; k < n_in; ++k) xf[k] = (double)h2f(x[k]);
 	for (int o = 0; o < n_out; ++o) {
 		double acc = 0.0;
 		const float* row = W + (size_t)o * n_in;
-		for (int k = 0; k < n_in; ++k) acc += (double)row[k] * xf[k];
+		if (g_mlp_policy == 1) {
+			uint16_t acc_h = 0;
+			for (int k0 = 0; k0 < n_in; k0 += 16) {
+				double part = 0.0;
+				for (int k = k0; k < k0 + 16 && k < n_in; ++k) part += (double)row[k] * xf[k];
+				acc_h = d2h((double)h2f(acc_h) + part);
+			}
+			acc = (double)h2f(acc_h);
+		} else {
+			for (int k = 0; k < n_in; ++k) acc += (double)row[k] * xf[k];
+		}
 		float a = (float)acc;
 		if (relu && !(a > 0.0f)) a = 0.0f;
 		y[o] = f2h(a);
@@ -664,6 +682,42 @@ struct Scene {
 // ========================================================================================
 // C entry points (ctypes)
 // ========================================================================================
+// ---- tcnn::default_rng_t = pcg32 (PCG-XSH-RR 64/32; public algorithm, tiny-cuda-nn pcg32.h [tcnn-ext]) -------------------
+// Pinned by the PCG reference known-answer vector (seed 42, stream 54) in tests/test_oracle_units.py.
+struct Pcg32 {
+	uint64_t state, inc;
+	uint32_t next_uint() {
+		uint64_t old = state;
+		state = old * 0x5851f42d4c957f2dULL + inc;
+		uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+		uint32_t rot = (uint32_t)(old >> 59u);
+		return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31u));
+	}
+	float next_float() {
+		uint32_t u = (next_uint() >> 9) | 0x3f800000u;
+		float f;
+		memcpy(&f, &u, 4);
+		return f - 1.0f;
+	}
+	void seed(uint64_t initstate, uint64_t initseq) {
+		state = 0u;
+		inc = (initseq << 1u) | 1u;
+		next_uint();
+		state += initstate;
+		next_uint();
+	}
+	void advance(uint64_t delta) {
+		uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+		while (delta > 0) {
+			if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+			cur_plus = (cur_mult + 1) * cur_plus;
+			cur_mult *= cur_mult;
+			delta >>= 1;
+		}
+		state = acc_mult * state + acc_plus;
+	}
+};
+
 extern "C" {
 
 typedef struct {
@@ -868,10 +922,21 @@ int orc_render(const OrcScene* s, const NsbFrame* f, float* fb, float* depth, Or
 				} else {
 					alpha = 1.0f - expf(-sigma * dtu);
 				}
+				if (f->show_accel) alpha = 1.0f;  // testbed_nerf.cu:788-790
 				float weight = alpha * T;
 				float rgb[3];
 				for (int c = 0; c < 3; ++c) rgb[c] = network_to_rgb(h2f(out[c]), f->rgb_activation);
 				if (f->render_mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
+				else if (f->render_mode == NSB_RENDER_POSITIONS && f->show_accel) {  // :913-923: one random colour per occupancy cell
+					uint32_t mip = (uint32_t)std::max(f->min_mip, mip_from_pos(cpos));
+					float res = (float)(GRIDSIZE >> mip);
+					int ix = (int)(cpos.x * res), iy = (int)(cpos.y * res), iz = (int)(cpos.z * res);
+					Pcg32 rng;  // tcnn::default_rng_t rng(seed) = pcg32::seed(initstate, 1)
+					rng.seed((uint64_t)(int64_t)(ix + iy * 232323 + iz * 727272), 1);
+					rgb[0] = 1.0f - (float)mip * 0.25f;
+					rgb[1] = rng.next_float();
+					rgb[2] = rng.next_float();
+				}
 				else if (f->render_mode == NSB_RENDER_POSITIONS) { rgb[0] = (cpos.x - 0.5f) / 2.0f + 0.5f; rgb[1] = (cpos.y - 0.5f) / 2.0f + 0.5f; rgb[2] = (cpos.z - 0.5f) / 2.0f + 0.5f; }
 				else if (f->render_mode == NSB_RENDER_DEPTH) { float z = dot3(cam_fwd, cpos - r.o) * f->depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
 				else if (f->render_mode == NSB_RENDER_DISTANCE) { V3 q = cpos - r.o; float z = sqrtf(dot3(q, q)) * f->depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
@@ -1014,41 +1079,6 @@ int orc_density_grid_to_bitfield(const float* grid /*5*128^3*/, uint8_t* bits /*
 	return 0;
 }
 
-// ---- tcnn::default_rng_t = pcg32 (PCG-XSH-RR 64/32; public algorithm, tiny-cuda-nn pcg32.h [tcnn-ext]) -------------------
-// Pinned by the PCG reference known-answer vector (seed 42, stream 54) in tests/test_oracle_units.py.
-struct Pcg32 {
-	uint64_t state, inc;
-	uint32_t next_uint() {
-		uint64_t old = state;
-		state = old * 0x5851f42d4c957f2dULL + inc;
-		uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
-		uint32_t rot = (uint32_t)(old >> 59u);
-		return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31u));
-	}
-	float next_float() {
-		uint32_t u = (next_uint() >> 9) | 0x3f800000u;
-		float f;
-		memcpy(&f, &u, 4);
-		return f - 1.0f;
-	}
-	void seed(uint64_t initstate, uint64_t initseq) {
-		state = 0u;
-		inc = (initseq << 1u) | 1u;
-		next_uint();
-		state += initstate;
-		next_uint();
-	}
-	void advance(uint64_t delta) {
-		uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
-		while (delta > 0) {
-			if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
-			cur_plus = (cur_mult + 1) * cur_plus;
-			cur_mult *= cur_mult;
-			delta >>= 1;
-		}
-		state = acc_mult * state + acc_plus;
-	}
-};
 void orc_pcg32_seed(uint64_t initstate, uint64_t initseq, uint64_t* state_inc /*2*/) {
 	Pcg32 r; r.seed(initstate, initseq);
 	state_inc[0] = r.state; state_inc[1] = r.inc;
@@ -1235,6 +1265,12 @@ int orc_membrane_blend(const float* gamma, uint32_t n_vertices, uint32_t n_cv, c
 		b_rd[i] = std::max(rd, 0.f);
 	}
 	return 0;
+}
+
+int orc_set_mlp_policy(int policy) {
+	int old = g_mlp_policy;
+	if (policy == 0 || policy == 1) g_mlp_policy = policy;
+	return old;
 }
 
 int orc_set_threads(int n) {

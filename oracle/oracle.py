@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
         l.orc_march_trace.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         l.orc_render.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbFrame), C.c_void_p, C.c_void_p, C.POINTER(OrcStats), C.c_void_p]
         l.orc_set_threads.argtypes = [C.c_int]
+        l.orc_set_mlp_policy.argtypes = [C.c_int]
         l.orc_density_grid_to_bitfield.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         l.orc_pcg32_seed.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
         l.orc_pcg32_seed.restype = None
@@ -228,6 +229,11 @@ def density_grid_to_bitfield(grid: np.ndarray):
     mean = C.c_float()
     assert lib().orc_density_grid_to_bitfield(_ptr(grid), _ptr(bits), C.byref(mean)) == 0
     return bits, mean.value
+
+
+def set_mlp_policy(policy: int) -> int:
+    """0 = wide accumulate (default), 1 = wmma __half accumulator fragments (round to fp16 after every k-chunk of 16). Returns the old policy."""
+    return lib().orc_set_mlp_policy(policy)
 
 
 def set_threads(n: int) -> int:

@@ -180,7 +180,7 @@ int ref_render(const NsbFrame* f, const uint8_t* bitfield, const NsbEditOp* ops,
 		tb.m_render_aabb = bb(f->render_aabb_min, f->render_aabb_max);
 		tb.m_aabb = bb(f->train_aabb_min, f->train_aabb_max);
 		tb.m_nerf.density_grid_bitfield.copy_from_host(bitfield, NSB_BITFIELD_BYTES);
-		tb.m_nerf.show_accel = f->min_mip > 0 ? f->min_mip : -1;
+		tb.m_nerf.show_accel = f->show_accel ? f->min_mip : -1;  // the reference derives min_mip from show_accel; without the override min_mip is 0
 		tb.m_nerf.cone_angle_constant = f->cone_angle_constant;
 		tb.m_nerf.training.dataset.scale = 1.0f / f->depth_scale;
 		tb.m_nerf.training.linear_colors = f->linear_colors != 0;

@@ -83,7 +83,7 @@ static void configure(RefCuScene& sc, const NsbFrame* f) {
 	tb.m_snap_to_pixel_centers = f->snap_to_pixel_centers != 0;
 	tb.m_render_aabb = bb(f->render_aabb_min, f->render_aabb_max);
 	tb.m_aabb = bb(f->train_aabb_min, f->train_aabb_max);
-	tb.m_nerf.show_accel = f->min_mip > 0 ? f->min_mip : -1;
+	tb.m_nerf.show_accel = f->show_accel ? f->min_mip : -1;  // the reference derives min_mip from show_accel; without the override min_mip is 0
 	tb.m_nerf.cone_angle_constant = f->cone_angle_constant;
 	tb.m_nerf.training.dataset.scale = 1.0f / f->depth_scale;
 	tb.m_nerf.training.linear_colors = f->linear_colors != 0;
