@@ -386,11 +386,25 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 			} else {
 				alpha = 1.0f - __expf(-sigma * dtu);
 			}
+			if (f.show_accel) alpha = 1.0f;  // show_accel >= 0: the occupancy cells themselves are drawn (:788-790)
 			float weight = alpha * T;
 			float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
 			if (f.mode != NSB_RENDER_SHADE) {
 				const V3 ro = v3(TB.ray[R_OX][tid], TB.ray[R_OY][tid], TB.ray[R_OZ][tid]);
 				if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
+				else if (f.mode == NSB_RENDER_POSITIONS && f.show_accel) {  // one random colour per occupancy cell (:913-923)
+					const uint32_t mip = (uint32_t)max(f.min_mip, mip_from_pos(cpos));
+					const float res = (float)(GRIDSIZE >> mip);
+					const int ix = (int)mul(cpos.x, res), iy = (int)mul(cpos.y, res), iz = (int)mul(cpos.z, res);
+					Pcg32 rng;  // tcnn::default_rng_t rng(seed): pcg32::seed(initstate, initseq = 1)
+					rng.state = 0; rng.inc = 3;
+					rng.next_uint();
+					rng.state += (uint64_t)(int64_t)(ix + iy * 232323 + iz * 727272);
+					rng.next_uint();
+					rgb[0] = fma_(-(float)mip, 0.25f, 1.0f);
+					rgb[1] = rng.next_float();
+					rgb[2] = rng.next_float();
+				}
 				else if (f.mode == NSB_RENDER_POSITIONS) { rgb[0] = (cpos.x - 0.5f) / 2.0f + 0.5f; rgb[1] = (cpos.y - 0.5f) / 2.0f + 0.5f; rgb[2] = (cpos.z - 0.5f) / 2.0f + 0.5f; }
 				else if (f.mode == NSB_RENDER_DEPTH) { float z = dot3(cam_fwd, vsub(cpos, ro)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
 				else if (f.mode == NSB_RENDER_DISTANCE) { V3 q = vsub(cpos, ro); float z = sqrtf(dot3(q, q)) * f.depth_scale; rgb[0] = rgb[1] = rgb[2] = z; }
@@ -923,7 +937,7 @@ struct NsbContext {
 	unsigned long long* d_stats = nullptr;
 	RayRec* d_list = nullptr;
 	size_t list_capacity = 0;
-	int acc16 = 0;                 // MLP accumulator policy: 0 fp32 TMEM accumulators, 1 fp16 (nsb_set_mlp_accumulator)
+	int acc16 = 1;                 // MLP accumulator policy: 1 fp16 TMEM accumulators (default: the reference's wmma __half fragments), 0 fp32 (nsb_set_mlp_accumulator)
 	int use_ws = 0;                // NSB_WS=1: frames without operators go through the warp-specialised kernel (experimental; default k_render_fused<false>)
 	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
 	int dda_budget = DDA_BUDGET;

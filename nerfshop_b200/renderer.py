@@ -52,7 +52,7 @@ class NerfRenderer:
         abi.check(self.lib, self.lib.nsb_upload_model(self.ctx, C.byref(desc), p.ctypes.data, p.size), "nsb_upload_model")
 
     def set_mlp_accumulator(self, policy: int):
-        """NSB_MLP_ACC_F32 (default) or NSB_MLP_ACC_F16 (the arithmetic of tiny-cuda-nn's wmma __half accumulator fragments)."""
+        """NSB_MLP_ACC_F16 (default: the arithmetic of tiny-cuda-nn's wmma __half accumulator fragments) or NSB_MLP_ACC_F32."""
         abi.check(self.lib, self.lib.nsb_set_mlp_accumulator(self.ctx, int(policy)), "nsb_set_mlp_accumulator")
 
     def upload_occupancy(self, bitfield: np.ndarray):

@@ -232,7 +232,7 @@ def density_grid_to_bitfield(grid: np.ndarray):
 
 
 def set_mlp_policy(policy: int) -> int:
-    """0 = wide accumulate (default), 1 = wmma __half accumulator fragments (round to fp16 after every k-chunk of 16). Returns the old policy."""
+    """1 = wmma __half accumulator fragments (round to fp16 after every k-chunk of 16; default), 0 = wide accumulate. Returns the old policy."""
     return lib().orc_set_mlp_policy(policy)
 
 

@@ -20,12 +20,13 @@ SHIM_MAIN = r'''
 #include "nerfshop_b200/host/nerfshop_host.hpp"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 static std::vector<char> slurp(const char* p) { FILE* f = fopen(p, "rb"); fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET); std::vector<char> b(n); fread(b.data(), 1, n, f); fclose(f); return b; }
 int main(int argc, char** argv) {
-  // argv: params.bin occupancy.bin frame.bin out.bin
-  auto params = slurp(argv[1]); auto occ = slurp(argv[2]); auto fr = slurp(argv[3]);
-  NsbModelDesc d{16, 2, 19, 16, 1.5157166f, 64, 1, 2, 4};
+  // argv: params.bin occupancy.bin frame.bin out.bin desc.bin
+  auto params = slurp(argv[1]); auto occ = slurp(argv[2]); auto fr = slurp(argv[3]); auto ds = slurp(argv[5]);
+  NsbModelDesc d; memcpy(&d, ds.data(), sizeof(d));
   NsbFrame frame; memcpy(&frame, fr.data(), sizeof(frame));
   auto ctx = std::make_shared<ngp_b200::Context>(0);
   ngp_b200::NerfNetwork net(ctx, d);
@@ -53,6 +54,7 @@ def test_cpp_shim_renders_the_same_frame(scene, renderer, built_lib, tmp_path):
     (tmp_path / "params.bin").write_bytes(np.ascontiguousarray(model.params, np.uint16).tobytes())
     (tmp_path / "occ.bin").write_bytes(np.ascontiguousarray(occ, np.uint8).tobytes())
     (tmp_path / "frame.bin").write_bytes(bytes(f))
+    (tmp_path / "desc.bin").write_bytes(bytes(model.desc))
     src = tmp_path / "main.cpp"
     src.write_text(SHIM_MAIN)
     exe = tmp_path / "shim_render"
@@ -60,7 +62,7 @@ def test_cpp_shim_renders_the_same_frame(scene, renderer, built_lib, tmp_path):
     cuda = "/usr/local/cuda"
     subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-I", ROOT, "-I", f"{cuda}/include", str(src), "-o", str(exe), "-L", libdir, "-lnerfshop_b200",
                     f"-Wl,-rpath,{libdir}", "-L", f"{cuda}/lib64", "-lcudart", f"-Wl,-rpath,{cuda}/lib64"], check=True)
-    out = subprocess.run([str(exe), str(tmp_path / "params.bin"), str(tmp_path / "occ.bin"), str(tmp_path / "frame.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, check=True)
+    out = subprocess.run([str(exe), str(tmp_path / "params.bin"), str(tmp_path / "occ.bin"), str(tmp_path / "frame.bin"), str(tmp_path / "out.bin"), str(tmp_path / "desc.bin")], capture_output=True, text=True, check=True)
     got = np.fromfile(tmp_path / "out.bin", np.float32)
     n = 160 * 90
     fb, depth = renderer.render(f)

@@ -23,7 +23,7 @@ def test_policies_differ_by_more_than_the_rgba_tolerance_on_a_few_pixels(scene):
         b, _, sb, _ = o.render(f)
         d = o.inference(np.random.default_rng(0).random((4096, 7), dtype=np.float32))
     finally:
-        orc.set_mlp_policy(0)
+        orc.set_mlp_policy(1)
     e = np.abs(a - b).max(-1)
     raw_equal = float((c == d).mean())
     print(f"\nwide vs half-accumulator: L-inf {e.max():.3e}, mean {e.mean():.2e}, pixels > 1e-3: {(e > 1e-3).sum()} of {e.size}, > 1e-4: {100 * (e > 1e-4).mean():.1f} %; "
@@ -52,9 +52,13 @@ def test_fp16_tmem_accumulators_match_the_half_fragment_policy(scene, renderer):
         fb_o, _, st, margin = o.render(f, want_margin=True)
         orc.set_mlp_policy(0)
         wide = o.inference(coords)
-    finally:
-        orc.set_mlp_policy(0)
+        # and the other policy pair: fp32 TMEM accumulators against the oracle's wide policy
         renderer.set_mlp_accumulator(abi.NSB_MLP_ACC_F32)
+        got32 = renderer.inference(coords)
+    finally:
+        orc.set_mlp_policy(1)
+        renderer.set_mlp_accumulator(abi.NSB_MLP_ACC_F16)
+    assert float((got32[:4] == wide[:4]).mean()) > 0.9
     g, w = got[:4].astype(np.int32), want[:4].astype(np.int32)
     ulp = np.abs(np.where(g & 0x8000, -(g & 0x7fff), g) - np.where(w & 0x8000, -(w & 0x7fff), w))
     eq = float((got[:4] == want[:4]).mean())

@@ -153,15 +153,22 @@ def test_trilinear_weights_and_hash_formula(scene):
 
 
 def test_inference_matches_numpy_mlp(scene, oracle):
-    """fp16 weights/activations, wide accumulation, fp16 rounding between layers (Appendix B)."""
+    """fp16 weights/activations, wmma __half accumulator fragments (the running sum is rounded to fp16 after every k-chunk of 16: Appendix B, the
+    oracle's default policy), fp16 rounding between layers."""
     model, _ = scene
     coords = random_coords(200, seed=4)
     enc = oracle.encode(coords).view(np.float16).astype(np.float64)  # [32, n]
     mlp = model.params[: syn.N_MLP_PARAMS].view(np.float16).astype(np.float64)
     W1, W2, W3, W4, W5 = (mlp[a:b].reshape(s) for a, b, s in ((0, 2048, (64, 32)), (2048, 3072, (16, 64)), (3072, 5120, (64, 32)), (5120, 9216, (64, 64)), (9216, 10240, (16, 64))))
     h = lambda a: a.astype(np.float32).astype(np.float16).astype(np.float64)  # noqa: E731
-    h1 = h(np.maximum(W1 @ enc, 0))
-    dens = h(W2 @ h1)
+    def mm(W, x):  # half accumulator fragments, m16n16k16
+        acc = np.zeros((W.shape[0], x.shape[1]))
+        for k0 in range(0, W.shape[1], 16):
+            acc = h(acc + W[:, k0:k0 + 16] @ x[k0:k0 + 16])
+        return acc
+
+    h1 = h(np.maximum(mm(W1, enc), 0))
+    dens = h(mm(W2, h1))
     d = coords[:, 4:].astype(np.float32) * np.float32(2.0) - np.float32(1.0)
     x, y, z = d[:, 0], d[:, 1], d[:, 2]
     sh = np.stack([
@@ -171,7 +178,7 @@ def test_inference_matches_numpy_mlp(scene, oracle):
         0.45704579946446572 * y * (1.0 - 5.0 * z * z), 0.3731763325901154 * z * (5.0 * z * z - 3.0), 0.45704579946446572 * x * (1.0 - 5.0 * z * z),
         1.4453057213202769 * z * (x * x - y * y), 0.59004358992664352 * x * (-x * x + 3.0 * y * y)]).astype(np.float32)
     rin = np.concatenate([dens, sh.astype(np.float16).astype(np.float64)], 0)
-    out = h(W5 @ h(np.maximum(W4 @ h(np.maximum(W3 @ rin, 0)), 0)))
+    out = h(mm(W5, h(np.maximum(mm(W4, h(np.maximum(mm(W3, rin), 0))), 0))))
     got = oracle.inference(coords).view(np.float16).astype(np.float64)
     gd = oracle.inference(coords, density_only=True).view(np.float16).astype(np.float64)
     assert np.abs(gd - dens).max() <= 1e-2 * np.abs(dens).max()  # float32-vs-double SH/accumulate noise flips an fp16 ulp at most
