@@ -260,11 +260,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-CUDA arm and the edit configurations (N = 1 extras)")
     args = ap.parse_args()
-    # pin the CPU arm's OpenMP threads (the round-1 arm swung 3.4x between two boxes with free-floating threads)
-    os.environ.setdefault("OMP_PROC_BIND", "close")
-    os.environ.setdefault("OMP_PLACES", "cores")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        # pin the CPU arm's OpenMP threads (the round-1 arm swung 3.4x between two boxes with free-floating threads). Single-process runs only:
+        # under torchrun every rank would bind its main thread to the same first core and the ranks' launch loops would time-share it.
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
+    else:
+        os.environ["NCCL_DEBUG"] = os.environ.get("NSB_NCCL_DEBUG", "WARN")  # rank 0 prints ONE JSON line: keep NCCL's version banner off stdout
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "nerf/fox 1080p free-viewpoint orbit, hash L=16 F=2 T=2^19, MLP 64x1 + 64x2 (configs[1])", "resolution": [W, H],
               "cameras": f"{N_ORBIT}-view orbit about (0.5, 0.5, 0.5), radius 1.45, height +0.35 (NGP units; closer than BASELINE.md's radius 2.0: more covered pixels, more samples per frame), look-at centre, focal 1080 px, one camera per step (index 7*step mod {N_ORBIT})", "parallelism": f"image-tile partition x{world}" if world > 1 else "single GPU"}
@@ -297,7 +301,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     model = syn.make_model(seed=1337)
     occ = syn.make_occupancy(model)
