@@ -268,7 +268,10 @@ def main():
         os.environ.setdefault("OMP_PROC_BIND", "close")
         os.environ.setdefault("OMP_PLACES", "cores")
     else:
-        os.environ["NCCL_DEBUG"] = os.environ.get("NSB_NCCL_DEBUG", "WARN")  # rank 0 prints ONE JSON line: keep NCCL's version banner off stdout
+        # rank 0 prints ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION or higher, set by some boxes) goes to stdout, so it is switched off
+        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("NSB_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["NSB_NCCL_DEBUG"]
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "nerf/fox 1080p free-viewpoint orbit, hash L=16 F=2 T=2^19, MLP 64x1 + 64x2 (configs[1])", "resolution": [W, H],
               "cameras": f"{N_ORBIT}-view orbit about (0.5, 0.5, 0.5), radius 1.45, height +0.35 (NGP units; closer than BASELINE.md's radius 2.0: more covered pixels, more samples per frame), look-at centre, focal 1080 px, one camera per step (index 7*step mod {N_ORBIT})", "parallelism": f"image-tile partition x{world}" if world > 1 else "single GPU"}

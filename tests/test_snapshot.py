@@ -91,3 +91,60 @@ def test_snapshot_to_render(tmp_path, scene, renderer):
         assert np.array_equal(r.upload_density_grid(g), orc.density_grid_to_bitfield(g)[0])
     finally:
         r.close()
+
+
+def test_reads_the_export_snapshot_schema(tmp_path, scene):
+    """Testbed::export_snapshot (testbed.cu:3118-3183): fp16 density grid of (max_cascade+1) cascades, aabb_scale at snapshot.nerf.aabb_scale, no dataset,
+    .ingp = the same stream behind zlib/gzip. Written here key by key from that function, then loaded."""
+    import zlib
+
+    import msgpack
+
+    model, occ = scene
+    grid = _grid_from_occupancy(occ)
+    n_casc = 3  # fox: max_cascade = 2
+    cfg = {"encoding": {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19, "base_resolution": 16},
+           "network": {"otype": "FullyFusedMLP", "n_neurons": 64, "n_hidden_layers": 1}, "rgb_network": {"otype": "FullyFusedMLP", "n_neurons": 64, "n_hidden_layers": 2},
+           "snapshot": {"version": 1, "n_params": int(model.params.size), "params_type": "__half", "params_binary": model.params.tobytes(),
+                        "density_grid_size": 128, "density_grid_binary": grid[: n_casc * 128 ** 3].astype(np.float16).tobytes(),
+                        "training_step": 35000, "loss": 0.001, "aabb": {"min": [-1.5] * 3, "max": [2.5] * 3},
+                        "nerf": {"aabb_scale": 4, "rgb": {"rays_per_batch": 4096, "measured_batch_size": 0, "measured_batch_size_before_compaction": 0}}}}
+    blob = msgpack.packb(cfg, use_bin_type=True)
+    co = zlib.compressobj(zlib.Z_DEFAULT_COMPRESSION, zlib.DEFLATED, 15 + 16)
+    path = tmp_path / "export.ingp"
+    path.write_bytes(co.compress(blob) + co.flush())
+    desc, params, g, aabb_scale = snapshot.load_snapshot(str(path))
+    assert aabb_scale == 4 and abs(desc.per_level_scale - model.desc.per_level_scale) < 1e-6  # derived like Testbed::reset_network (the file has none)
+    assert np.array_equal(params, model.params)
+    assert np.array_equal(g[: n_casc * 128 ** 3], grid[: n_casc * 128 ** 3]) and not g[n_casc * 128 ** 3:].any()
+    bits, _ = orc.density_grid_to_bitfield(g)
+    assert np.array_equal(bits[: n_casc * 128 ** 3 // 8], occ[: n_casc * 128 ** 3 // 8])
+
+
+def test_written_snapshot_has_every_key_the_reference_reads(tmp_path, scene):
+    """save_snapshot's file must survive Testbed::load_snapshot: NerfDataset::from_json (json_binding.h:164-194) reads these keys with .at()."""
+    import msgpack
+
+    model, occ = scene
+    path = str(tmp_path / "full.msgpack")
+    snapshot.save_snapshot(path, model.desc, model.params, _grid_from_occupancy(occ), model.aabb_scale)
+    cfg = msgpack.unpackb(open(path, "rb").read(), raw=False)
+    ds = cfg["snapshot"]["nerf"]["dataset"]
+    for key in ("n_images", "xforms", "render_aabb", "up", "offset", "image_resolution", "envmap_resolution", "scale", "aabb_scale", "from_mitsuba"):
+        assert key in ds, key
+    assert ds["n_images"] == 0 and ds["xforms"] == [] and ds["render_aabb"]["min"] == [-1.5] * 3 and ds["render_aabb"]["max"] == [2.5] * 3
+    assert cfg["snapshot"]["nerf"]["aabb_scale"] == 4 and cfg["snapshot"]["density_grid_size"] == 128
+    for key in ("rays_per_batch", "measured_batch_size", "measured_batch_size_before_compaction"):  # testbed.cu:3064-3066
+        assert key in cfg["snapshot"]["nerf"]["rgb"]
+
+
+def test_missing_aabb_scale_is_an_error(tmp_path, scene):
+    import msgpack
+
+    model, occ = scene
+    cfg = {"encoding": {}, "network": {}, "rgb_network": {}, "snapshot": {"n_params": 0, "params_type": "__half", "params_binary": b"", "density_grid_size": 128,
+                                                                          "density_grid_binary": b"", "nerf": {"rgb": {}}}}
+    p = tmp_path / "bad.msgpack"
+    p.write_bytes(msgpack.packb(cfg, use_bin_type=True))
+    with pytest.raises(abi.NsbError, match="aabb_scale"):
+        snapshot.load_snapshot(str(p))

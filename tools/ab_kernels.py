@@ -58,6 +58,8 @@ for spec in sys.argv[1:]:
     if parts[0]:
         env["NSB_LIB_PATH"] = os.path.join(ROOT, parts[0]) if not os.path.isabs(parts[0]) else parts[0]
     for kv in parts[1:]:
+        if not kv:
+            continue
         k, v = kv.split("=")
         env[k] = v
     res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True, text=True, timeout=600)
