@@ -120,6 +120,17 @@ __device__ __forceinline__ void encode_to_a32(uint8_t* a32, const DevModel& m, b
 __device__ __forceinline__ float h_lo(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed & 0xffffu))); }
 __device__ __forceinline__ float h_hi(uint32_t packed) { return __half2float(__ushort_as_half((unsigned short)(packed >> 16))); }
 
+// position of the k-th (0-based) set bit of m; popc(m) > k
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t k) {
+	uint32_t p = 0;
+#pragma unroll
+	for (uint32_t s = 16; s >= 1; s >>= 1) {
+		const uint32_t c = (uint32_t)__popc((m >> p) & ((1u << s) - 1u));
+		if (k >= c) { k -= c; p += s; }
+	}
+	return p;
+}
+
 // Stage 2 (persistent; a tile = 128 threads = 128 ray slots = 128 MMA rows, NSB_TILES tiles per CTA): every round each live ray contributes
 // ONE sample; samples go deform -> hash encode -> tcgen05 MLPs -> composite inside the SM; a finished ray is shaded
 // into the framebuffer and its slot refilled from the queue (warp-convergent fetch of consecutive entries, so rays that
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
                                                       float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
                                                       const uint32_t* __restrict__ n_queued_ptr, uint32_t* fetch_counter,
-                                                      unsigned long long* __restrict__ stats, const int refill_thr, const int dda_budget) {
+                                                      unsigned long long* __restrict__ stats, const int refill_thr, const int dda_flags) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	RenderSmem& RS = *reinterpret_cast<RenderSmem*>(smem_raw);
 	const uint32_t tid = threadIdx.x & 127u;      // slot / row within the tile
@@ -193,6 +204,22 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	C.a32 = TB.a32; C.a64 = TB.a64; C.w_addr = tc::smem_u32(RS.w); C.mma_bar = &TB.mma_bar; C.tmem = tmem_base + tile * tc::TMEM_COLS; C.row = tid;
 	C.bar_id = 1 + tile;
 
+	const int dda_budget = dda_flags & 0xffff;
+	// Helper lanes (frames without operators). A round costs the same ~20 K cycles whether 32 or 3 lanes of a warp carry a sample, and a warp only
+	// refills once it is down to refill_thr rays, so the lanes WITHOUT a ray are lent to the rays that found a sample this round: each such ray gets up
+	// to HELP_DEPTH of them, and helper j evaluates the ray's j-th NEXT sample (t advanced j times by calc_dt, its own occupancy test) through the
+	// encode and the MLPs. The owner lane then composites its own sample and, in march order, the helpers' — up to the first one that was not an
+	// occupied in-bounds sample, where the ordinary march resumes next round. Samples past a ray's termination are evaluated and discarded, like the
+	// reference's own n_steps > 1 batching; frames are bit-identical with or without helpers. help_mode 1: only once the queue is exhausted, 2: always.
+	// MEASURED (profiles/README.md, round 2): 13.5 % fewer rounds but each round 27 % dearer — the loop's cost follows the samples evaluated (gather
+	// wavefronts + issue), not the rounds — so the default is 0 and this stays an opt-in experiment.
+	const int help_mode = OPS ? 0 : (dda_flags >> 16) & 3;  // host: NSB_HELPERS
+	constexpr uint32_t HELP_DEPTH = 7;
+	// mailbox helper -> owner: the tile's A-operand buffer is idle between the last MMA of a round and the next encode, and every warp only ever
+	// writes its own 32 rows of it: field q of lane l lives in k-chunk q, at this warp's 512 bytes
+	float* const mbox = reinterpret_cast<float*>(TB.a64 + (tid >> 5) * 512u) + lane;
+	constexpr uint32_t MB = tc::ROWS * 16 / 4;  // floats between mailbox fields
+	enum { M_ALPHA = 0, M_E0, M_E1, M_E2, M_Z, M_TNEXT };  // M_TNEXT < 0: not a sample
 	constexpr bool ops_on = OPS;  // the host picks the instantiation: f.apply_ops && n_ops > 0
 
 	// what stays in registers across a round
@@ -240,6 +267,10 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 		bool has_sample = false;
 		float dt = 0.0f;
 		V3 pos = v3(0, 0, 0), dw = v3(0.5f, 0.5f, 0.5f);
+		int h_owner = -1;                  // >= 0: this lane helps the ray of that lane this round
+		float h_tnext = -1.0f;             // helper: t after its sample
+		unsigned h_free = 0u;              // warp-uniform: the helper lanes of this round (0: none)
+		uint32_t h_per_ray = 0, h_first = 0;  // owner: its helpers are the h_per_ray free lanes from free-rank h_first
 		{
 			int budget = dda_budget;
 			V3 ro = v3(TB.ray[R_OX][tid], TB.ray[R_OY][tid], TB.ray[R_OZ][tid]);
@@ -303,6 +334,43 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 				t = add(t, dt);
 			}
 			if (alive) TB.ray[R_T][tid] = t;
+			if constexpr (!OPS) {
+				if (help_mode == 2 || (help_mode == 1 && exhausted)) {
+					const unsigned smp_m = __ballot_sync(0xffffffffu, has_sample);  // rays that found a sample this round
+					const unsigned free_m = ~__ballot_sync(0xffffffffu, alive);     // lanes without a ray
+					const uint32_t n_smp = (uint32_t)__popc(smp_m), n_free = (uint32_t)__popc(free_m);
+					if (n_smp != 0u && n_free != 0u) {
+						h_free = free_m;
+						h_per_ray = n_free >= n_smp ? min(HELP_DEPTH, n_free / n_smp) : 1u;  // fewer free lanes than rays: the first n_free rays get one each
+						uint32_t depth = 0;
+						if (!alive) {
+							const uint32_t q = (uint32_t)__popc(free_m & ((1u << lane) - 1u));
+							const uint32_t k = q / h_per_ray;
+							if (k < n_smp) { h_owner = (int)nth_set_bit(smp_m, k); depth = 1u + q % h_per_ray; }
+						} else if (has_sample) {
+							h_first = (uint32_t)__popc(smp_m & ((1u << lane) - 1u)) * h_per_ray;
+							if (h_first >= n_free) h_per_ray = 0;
+						}
+						const int sl = h_owner < 0 ? (int)lane : h_owner;
+						const V3 hro = v3(__shfl_sync(0xffffffffu, ro.x, sl), __shfl_sync(0xffffffffu, ro.y, sl), __shfl_sync(0xffffffffu, ro.z, sl));
+						const V3 hrd = v3(__shfl_sync(0xffffffffu, rd.x, sl), __shfl_sync(0xffffffffu, rd.y, sl), __shfl_sync(0xffffffffu, rd.z, sl));
+						float tj = __shfl_sync(0xffffffffu, t, sl);                  // the owner's t after its own sample
+						const uint32_t hsteps = __shfl_sync(0xffffffffu, n_steps, sl);  // ... and its step count before it
+						if (h_owner >= 0) {
+							for (uint32_t i = 1; i < depth; ++i) tj = add(tj, calc_dt(tj, f.cone));  // the march of :671-688 over occupied samples
+							pos = madd3(hrd, tj, hro);
+							bool ok = hsteps + depth < MARCH_ITER - 1 && box_contains(f.rmin, f.rmax, pos);
+							dt = calc_dt(tj, f.cone);
+							if (ok && bitfield) {
+								const uint32_t mip = (uint32_t)max(f.min_mip, mip_from_dt(dt, pos));
+								ok = bitfield_at(cascaded_grid_idx_at(pos, mip), mip, bitfield);
+							}
+							has_sample = ok;
+							if (ok) { dw = warp_direction(hrd); h_tnext = add(tj, dt); }
+						}
+					}
+				}
+			}
 		}
 
 		// ---- network inputs: generate_next_nerf_network_inputs :690 ----
@@ -316,8 +384,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 		if (has_sample) {
 			pw = warp_position(pos, f.tmin, f.tmax);
 			dtw = warp_dt(dt);
-			++n_steps;
-			++c_samples;
+			if (h_owner < 0) { ++n_steps; ++c_samples; }  // a helper's sample is counted by the owner when it composites it
 			if (ops_on) {
 				if (any_poisson) {  // membrane residuals are evaluated in deformed space (:2867-2883)
 					poisson_one(ops, n_ops, pw, mem);
@@ -360,14 +427,12 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 		const long long c3 = clock64();
 #endif
 
-		// ---- composite_kernel_nerf :750-955 for this one sample ----
+		// ---- composite_kernel_nerf :750-955, split in two: what depends on the sample alone (any lane), then the ray's running sums (its owner lane) ----
+		float s_alpha = 0.0f, s_e[3] = {0.0f, 0.0f, 0.0f}, s_z = 0.0f;
 		if (has_sample) {
-			const float sat = 1.0f - f.min_T;  // rendering_min_transmittance test of composite_kernel_nerf :951
+			const uint32_t rtid = h_owner < 0 ? tid : (tid & ~31u) + (uint32_t)h_owner;  // the slot of the ray this sample belongs to
 			const V3 cam_fwd = v3(f.cam1[6], f.cam1[7], f.cam1[8]);
-			float cr = TB.ray[R_CR][tid], cg = TB.ray[R_CG][tid], cb = TB.ray[R_CB][tid], ca = TB.ray[R_CA][tid];
-			float ray_depth = TB.ray[R_DEPTH][tid], max_weight = TB.ray[R_MAXW][tid];
 			V3 cpos = unwarp_position(pw, f.tmin, f.tmax);
-			float T = 1.0f - ca;
 			float dtu = unwarp_dt(dtw);
 			float sigma = network_to_density(h_lo(dens[0]), f.density_act);  // row 3 = density MLP out[0] (extract_density)
 			float alpha;
@@ -387,10 +452,9 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 				alpha = 1.0f - __expf(-sigma * dtu);
 			}
 			if (f.show_accel) alpha = 1.0f;  // show_accel >= 0: the occupancy cells themselves are drawn (:788-790)
-			float weight = alpha * T;
 			float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
 			if (f.mode != NSB_RENDER_SHADE) {
-				const V3 ro = v3(TB.ray[R_OX][tid], TB.ray[R_OY][tid], TB.ray[R_OZ][tid]);
+				const V3 ro = v3(TB.ray[R_OX][rtid], TB.ray[R_OY][rtid], TB.ray[R_OZ][rtid]);
 				if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
 				else if (f.mode == NSB_RENDER_POSITIONS && f.show_accel) {  // one random colour per occupancy cell (:913-923)
 					const uint32_t mip = (uint32_t)max(f.min_mip, mip_from_pos(cpos));
@@ -416,24 +480,61 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 				float w_N = alpha_N / (alpha_N + alpha_R), w_R = alpha_R / (alpha_N + alpha_R);
 				float res[3];
 				membrane_rgb(ops, mem, unwarp_direction(dw), res);
-				cr = __fmaf_rn(weight, __fmaf_rn(w_R, res[0], w_N * rgb[0]), cr);
-				cg = __fmaf_rn(weight, __fmaf_rn(w_R, res[1], w_N * rgb[1]), cg);
-				cb = __fmaf_rn(weight, __fmaf_rn(w_R, res[2], w_N * rgb[2]), cb);
-			} else {
-				cr = __fmaf_rn(rgb[0], weight, cr);
-				cg = __fmaf_rn(rgb[1], weight, cg);
-				cb = __fmaf_rn(rgb[2], weight, cb);
+				rgb[0] = __fmaf_rn(w_R, res[0], w_N * rgb[0]);
+				rgb[1] = __fmaf_rn(w_R, res[1], w_N * rgb[1]);
+				rgb[2] = __fmaf_rn(w_R, res[2], w_N * rgb[2]);
 			}
-			ca += weight;
-			if (weight > max_weight) {
-				max_weight = weight;
-				ray_depth = dot3(cam_fwd, vsub(cpos, v3(f.cam1[9], f.cam1[10], f.cam1[11])));
+			s_alpha = alpha; s_e[0] = rgb[0]; s_e[1] = rgb[1]; s_e[2] = rgb[2];
+			s_z = dot3(cam_fwd, vsub(cpos, v3(f.cam1[9], f.cam1[10], f.cam1[11])));
+		}
+		if constexpr (!OPS) {
+			if (h_free) {  // warp-uniform: helpers post their samples, owners read them below
+				if (h_owner >= 0) {
+					mbox[M_TNEXT * MB] = h_tnext;
+					if (has_sample) { mbox[M_ALPHA * MB] = s_alpha; mbox[M_E0 * MB] = s_e[0]; mbox[M_E1 * MB] = s_e[1]; mbox[M_E2 * MB] = s_e[2]; mbox[M_Z * MB] = s_z; }
+				}
+				__syncwarp();
 			}
-			if (ca > sat) {
-				float a = ca;
-				cr = __fdiv_rn(cr, a); cg = __fdiv_rn(cg, a); cb = __fdiv_rn(cb, a); ca = __fdiv_rn(ca, a);
-				finish(false, cr, cg, cb, ca, ray_depth);
-			} else {
+		}
+		if (has_sample && h_owner < 0) {
+			const float sat = 1.0f - f.min_T;  // rendering_min_transmittance test of composite_kernel_nerf :951
+			float cr = TB.ray[R_CR][tid], cg = TB.ray[R_CG][tid], cb = TB.ray[R_CB][tid], ca = TB.ray[R_CA][tid];
+			float ray_depth = TB.ray[R_DEPTH][tid], max_weight = TB.ray[R_MAXW][tid];
+			auto accumulate = [&](const float alpha, const float e0, const float e1, const float e2, const float z) {
+				float T = 1.0f - ca;
+				float weight = alpha * T;
+				cr = __fmaf_rn(e0, weight, cr);
+				cg = __fmaf_rn(e1, weight, cg);
+				cb = __fmaf_rn(e2, weight, cb);
+				ca += weight;
+				if (weight > max_weight) {
+					max_weight = weight;
+					ray_depth = z;
+				}
+				if (ca > sat) {
+					float a = ca;
+					cr = __fdiv_rn(cr, a); cg = __fdiv_rn(cg, a); cb = __fdiv_rn(cb, a); ca = __fdiv_rn(ca, a);
+					finish(false, cr, cg, cb, ca, ray_depth);
+				}
+			};
+			accumulate(s_alpha, s_e[0], s_e[1], s_e[2], s_z);
+			if constexpr (!OPS) {
+				if (h_free && h_per_ray) {  // this ray's helpers: consecutive free lanes from free-rank h_first, in march order
+					const float* wbox = mbox - lane;
+					uint32_t hl = nth_set_bit(h_free, h_first);
+					const uint32_t n_free = (uint32_t)__popc(h_free);
+					for (uint32_t i = 0; alive && i < h_per_ray && h_first + i < n_free; ++i) {
+						const float tn = wbox[M_TNEXT * MB + hl];
+						if (tn < 0.0f) break;  // not an occupied in-bounds sample: the march resumes there next round
+						++n_steps;
+						++c_samples;
+						accumulate(wbox[M_ALPHA * MB + hl], wbox[M_E0 * MB + hl], wbox[M_E1 * MB + hl], wbox[M_E2 * MB + hl], wbox[M_Z * MB + hl]);
+						TB.ray[R_T][tid] = tn;
+						hl = (uint32_t)__ffs((int)(h_free & ~((2u << hl) - 1u))) - 1u;  // next free lane
+					}
+				}
+			}
+			if (alive) {
 				TB.ray[R_CR][tid] = cr; TB.ray[R_CG][tid] = cg; TB.ray[R_CB][tid] = cb; TB.ray[R_CA][tid] = ca;
 				TB.ray[R_DEPTH][tid] = ray_depth; TB.ray[R_MAXW][tid] = max_weight;
 			}
@@ -939,6 +1040,7 @@ struct NsbContext {
 	size_t list_capacity = 0;
 	int acc16 = 1;                 // MLP accumulator policy: 1 fp16 TMEM accumulators (default: the reference's wmma __half fragments), 0 fp32 (nsb_set_mlp_accumulator)
 	int use_ws = 0;                // NSB_WS=1: frames without operators go through the warp-specialised kernel (experimental; default k_render_fused<false>)
+	int helpers = 0;               // helper lanes of k_render_fused (frames without operators; experiment, measured slower: profiles/README.md): 0 off (default), 1 once the queue is exhausted, 2 always (NSB_HELPERS)
 	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
 	int dda_budget = DDA_BUDGET;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;  // start, end, between k_prepare_rays and k_render_fused
@@ -1060,6 +1162,7 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	if (const char* e = getenv("NSB_WS")) c->use_ws = atoi(e) != 0;
 	if (const char* e = getenv("NSB_MLP_ACC16")) c->acc16 = atoi(e) != 0;
 	if (const char* e = getenv("NSB_REFILL_THR")) { int v = atoi(e); if (v >= 0 && v <= 31) c->refill_thr = v; }
+	if (const char* e = getenv("NSB_HELPERS")) { int v = atoi(e); if (v >= 0 && v <= 2) c->helpers = v; }
 	if (const char* e = getenv("NSB_CHUNK")) { int v = atoi(e); if (v >= 0 && v <= 65535) c->refill_thr |= v << 8; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
 	if (getenv("NSB_VERBOSE"))
@@ -1690,7 +1793,7 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		auto kernel = ops_on ? (c->acc16 ? k_render_fused<true, true> : k_render_fused<true, false>) : (c->acc16 ? k_render_fused<false, true> : k_render_fused<false, false>);
 		kernel<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
 		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
-		                                                          c->refill_thr, c->dda_budget);
+		                                                          c->refill_thr, c->dda_budget | (c->helpers << 16));
 		}
 		CU(cudaGetLastError());
 	}

@@ -227,6 +227,42 @@ def test_full_size_properties(scene, renderer):
     assert st1.n_samples > 20 * st1.n_hit * 0.2
 
 
+def test_helper_lanes_do_not_change_the_frame(scene, monkeypatch):
+    """k_render_fused lends the lanes without a ray to the rays that have one (up to 7 further samples per ray and round, composited in march
+    order by the ray's own lane; NSB_HELPERS, an opt-in experiment). Scheduling only: frames, depth and the ray / sample / hit counts are bit-identical
+    with helpers off (0, the default), in the frame's tail only (1) and always (2) — at 1080p, at a ragged size, on a tile partition and in every render mode."""
+    import torch
+
+    from nerfshop_b200.renderer import NerfRenderer
+
+    model, occ = scene
+    cams = syn.orbit_cameras(120)
+    jobs = [(syn.make_frame(model, cams[17], 1920, 1080), "1080p"), (syn.make_frame(model, cams[44], 333, 187), "ragged"),
+            (syn.make_frame(model, cams[80], 640, 360, rank=3, world=8), "partition")]
+    for mode in (abi.NSB_RENDER_AO, abi.NSB_RENDER_POSITIONS, abi.NSB_RENDER_DEPTH, abi.NSB_RENDER_STEPSIZE, abi.NSB_RENDER_COST):
+        f = syn.make_frame(model, cams[5], 480, 270)
+        f.mode = mode
+        jobs.append((f, f"mode {mode}"))
+    results = {}
+    for helpers in ("0", "1", "2"):
+        monkeypatch.setenv("NSB_HELPERS", helpers)
+        r = NerfRenderer(0)
+        r.upload_model(model.desc, model.params)
+        r.upload_occupancy(occ)
+        out = []
+        for f, _ in jobs:
+            fb, d = r.render(f)
+            st = r.stats()
+            out.append((fb.clone(), d.clone(), (st.n_rays, st.n_samples, st.n_hit)))
+        torch.cuda.synchronize()
+        results[helpers] = out
+        r.close()
+    for helpers in ("1", "2"):
+        for (fb0, d0, st0), (fb, d, st), (_, name) in zip(results["0"], results[helpers], jobs):
+            assert st == st0, (helpers, name, st, st0)
+            assert torch.equal(fb, fb0) and torch.equal(d, d0), (helpers, name)
+
+
 def test_no_model_is_an_error(built_lib):
     import ctypes as C
 
