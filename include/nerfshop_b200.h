@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NSB_ABI_VERSION 2
+#define NSB_ABI_VERSION 3
 
 /* reference: common_nerf.h:16-39 */
 #define NSB_NERF_GRIDSIZE 128u
@@ -59,6 +59,7 @@ typedef enum {
 	NSB_RENDER_DEPTH = 4,
 	NSB_RENDER_DISTANCE = 5,
 	NSB_RENDER_STEPSIZE = 6,
+	NSB_RENDER_DISTORTION = 7, /* the distortion map itself, written by ray initialisation (testbed_nerf.cu:2596-2607) */
 	NSB_RENDER_COST = 8
 } NsbRenderMode;
 
@@ -116,7 +117,31 @@ typedef struct {
 	/* m_nerf.show_accel >= 0 (the GUI's occupancy-grid visualisation): 0 = off (the reference's -1); 1 = on with show_accel = min_mip: every sample's
 	 * alpha is forced to 1 (testbed_nerf.cu:788-790) and Positions mode colours the occupancy cells (:913-923). Zero-initialised frames have it off. */
 	int32_t  show_accel;
+	/* ---- ABI 3: the remaining arguments of init_rays_with_payload_kernel_nerf / pixel_to_ray / composite_kernel_nerf. All zero = off. ---- */
+	/* m_nerf.render_with_camera_distortion ? m_nerf.render_distortion : CameraDistortion{} (testbed_nerf.cu:3081,3096; common.h:166-175;
+	 * pixel_to_ray common_device.cuh:263-277): NsbCameraDistortionMode; params = {k1, k2, p1, p2} (iterative OpenCV undistortion, :163-197)
+	 * or {r0..r4, res_x, res_y} (f-theta, :232-245) */
+	int32_t  camera_distortion_mode;
+	float    camera_distortion_params[7];
+	/* depth of field (pixel_to_ray :285-294): dof = m_dof (aperture), focus_z = m_slice_plane_z + m_scale (> 0; the Slice side path, which the
+	 * reference selects with a negative plane_z, is not covered). dof == 0: pinhole, focus_z unused. */
+	float    dof;
+	float    focus_z;
+	/* m_nerf.m_glow_mode / m_glow_y_cutoff (composite_kernel_nerf :807-903): bit 0 green grid, 1 cut line, 2 mask to alpha, 3 radial, 4 grid mode */
+	int32_t  glow_mode;
+	float    glow_y_cutoff;
+	/* m_envmap (init_rays :2581-2583, envmap.cuh:30-62): float RGBA texels in DEVICE memory, row-major [res_y][res_x][4]; when set, every pixel of
+	 * the frame buffer is first overwritten with the environment colour of its ray (the frame is then blended over it). NULL: the buffer is kept. */
+	const float* envmap_dev;
+	int32_t  envmap_resolution[2];
+	/* m_distortion.map (pixel_to_ray :278-280, read_image common_device.cuh:79-110): float2 texels in DEVICE memory added to the camera-space ray
+	 * direction; also what NSB_RENDER_DISTORTION visualises (init_rays :2596-2607). NULL: none. */
+	const float* distortion_dev;
+	int32_t  distortion_resolution[2];
 } NsbFrame;
+
+/* reference: common.h:166-170 (ECameraDistortionMode) */
+typedef enum { NSB_CAMERA_DISTORTION_NONE = 0, NSB_CAMERA_DISTORTION_ITERATIVE = 1, NSB_CAMERA_DISTORTION_FTHETA = 2 } NsbCameraDistortionMode;
 
 typedef enum { NSB_OP_CAGE = 0, NSB_OP_AFFINE = 1 } NsbEditOpType;
 

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnerfshop_b200.so")
 
-NSB_ABI_VERSION = 2
+NSB_ABI_VERSION = 3
 NSB_MLP_ACC_F32, NSB_MLP_ACC_F16 = 0, 1
 NSB_NERF_GRIDSIZE = 128
 NSB_NERF_CASCADES = 5
@@ -26,7 +26,9 @@ NSB_RENDER_POSITIONS = 3
 NSB_RENDER_DEPTH = 4
 NSB_RENDER_DISTANCE = 5
 NSB_RENDER_STEPSIZE = 6
+NSB_RENDER_DISTORTION = 7
 NSB_RENDER_COST = 8
+NSB_CAMERA_DISTORTION_NONE, NSB_CAMERA_DISTORTION_ITERATIVE, NSB_CAMERA_DISTORTION_FTHETA = range(3)
 
 NSB_ACT_NONE, NSB_ACT_RELU, NSB_ACT_LOGISTIC, NSB_ACT_EXPONENTIAL = range(4)
 NSB_OP_CAGE, NSB_OP_AFFINE = 0, 1
@@ -56,6 +58,12 @@ class NsbFrame(C.Structure):
         ("spp_index", u32), ("snap_to_pixel_centers", i32), ("apply_operators", i32),
         ("poisson_target", i32), ("linear_colors", i32), ("min_mip", i32),
         ("tile_rank", i32), ("tile_world", i32), ("show_accel", i32),
+        # ABI 3 (all zero = off)
+        ("camera_distortion_mode", i32), ("camera_distortion_params", f32 * 7),
+        ("dof", f32), ("focus_z", f32),
+        ("glow_mode", i32), ("glow_y_cutoff", f32),
+        ("envmap_dev", C.c_void_p), ("envmap_resolution", i32 * 2),
+        ("distortion_dev", C.c_void_p), ("distortion_resolution", i32 * 2),
     ]
 
 

@@ -57,6 +57,15 @@ struct DevFrame {
 	int apply_ops, poisson_target, linear_colors, min_mip, show_accel;
 	int tile_rank, tile_world;
 	int tiles_x, tiles_y;
+	// ABI 3: the general camera of pixel_to_ray, glow, environment map (all off = the fields above describe the frame completely)
+	int general_camera;        // lens distortion, distortion map or depth of field: make_ray_general instead of make_ray
+	int cam_dist_mode;         // ECameraDistortionMode
+	float cam_dist[7];
+	float dof, focus_z;
+	int glow_mode;
+	float glow_y_cutoff;
+	const float* envmap; int env_w, env_h;
+	const float* distortion; int dist_w, dist_h;
 };
 
 struct DevAffineBox { float mn[3], u[3], v[3], w[3], c[3]; };
@@ -303,6 +312,195 @@ __device__ __forceinline__ bool make_ray(const DevFrame& f, uint32_t px, uint32_
 	if (!box_contains(f.rmin, f.rmax, madd3(r.d, t, r.o))) return false;
 	r.t = t;
 	return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The general camera: pixel_to_ray with lens distortion, a distortion map and depth of field (common_device.cuh:79-110,145-295),
+// square2disk_shirley / ld_random_val_2d (random_val.cuh:109-127,278-282). Only k_prepare_rays<true> / k_march_trace<true> contain it: frames that
+// ask for it hand the persistent renderer their rays through a side buffer; plain fp32 with the compiler's own contraction, like the reference's: these frames are held to the
+// 1e-3 frame tolerance, not to bit-exact ray generation (Newton iterations, sincosf).
+// ------------------------------------------------------------------------------------------------
+__device__ const uint32_t c_sobol_dir1[32] = {
+	0x80000000u, 0xc0000000u, 0xa0000000u, 0xf0000000u, 0x88000000u, 0xcc000000u, 0xaa000000u, 0xff000000u, 0x80800000u, 0xc0c00000u, 0xa0a00000u,
+	0xf0f00000u, 0x88880000u, 0xcccc0000u, 0xaaaa0000u, 0xffff0000u, 0x80008000u, 0xc000c000u, 0xa000a000u, 0xf000f000u, 0x88008800u, 0xcc00cc00u,
+	0xaa00aa00u, 0xff00ff00u, 0x80808080u, 0xc0c0c0c0u, 0xa0a0a0a0u, 0xf0f0f0f0u, 0x88888888u, 0xccccccccu, 0xaaaaaaaau, 0xffffffffu,
+};
+__device__ __forceinline__ void ld_random_val_2d(uint32_t index, uint32_t seed, float& x, float& y) {
+	index = nested_uniform_scramble_base2(index, seed);
+	uint32_t X1 = 0;
+	for (uint32_t bit = 0; bit < 32; ++bit) X1 ^= ((index >> bit) & 1u) * c_sobol_dir1[bit];
+	x = (float)nested_uniform_scramble_base2(reverse_bits(index), hash_combine(seed, 0)) * 2.3283064365386963e-10f;
+	y = (float)nested_uniform_scramble_base2(X1, hash_combine(seed, 1)) * 2.3283064365386963e-10f;
+}
+__device__ __forceinline__ void apply_camera_distortion(const float* p, float u, float v, float& du, float& dv) {  // :145-160
+	const float k1 = p[0], k2 = p[1], p1 = p[2], p2 = p[3];
+	const float u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2;
+	const float radial = k1 * r2 + k2 * r2 * r2;
+	du = u * radial + 2.0f * p1 * uv + p2 * (r2 + 2.0f * u2);
+	dv = v * radial + 2.0f * p2 * uv + p1 * (r2 + 2.0f * v2);
+}
+__device__ __forceinline__ void iterative_camera_undistortion(const float* params, float& u, float& v) {  // :163-197
+	const float x0 = u, y0 = v;
+	float x = u, y = v;
+	for (uint32_t i = 0; i < 100u; ++i) {
+		const float step0 = fmaxf(1.1920928955078125e-7f, fabsf(1e-6f * x));
+		const float step1 = fmaxf(1.1920928955078125e-7f, fabsf(1e-6f * y));
+		float dx, dy, dx0b, dy0b, dx0f, dy0f, dx1b, dy1b, dx1f, dy1f;
+		apply_camera_distortion(params, x, y, dx, dy);
+		apply_camera_distortion(params, x - step0, y, dx0b, dy0b);
+		apply_camera_distortion(params, x + step0, y, dx0f, dy0f);
+		apply_camera_distortion(params, x, y - step1, dx1b, dy1b);
+		apply_camera_distortion(params, x, y + step1, dx1f, dy1f);
+		const float j00 = 1.0f + (dx0f - dx0b) / (2.0f * step0), j01 = (dx1f - dx1b) / (2.0f * step1);
+		const float j10 = (dy0f - dy0b) / (2.0f * step0), j11 = 1.0f + (dy1f - dy1b) / (2.0f * step1);
+		const float rx = x + dx - x0, ry = y + dy - y0;
+		const float invdet = 1.0f / (j00 * j11 - j10 * j01);  // Eigen's 2x2 inverse: adjugate times 1/det
+		const float sx = (j11 * invdet) * rx + (-j01 * invdet) * ry;
+		const float sy = (-j10 * invdet) * rx + (j00 * invdet) * ry;
+		x -= sx; y -= sy;
+		if (sx * sx + sy * sy < 1e-10f) break;
+	}
+	u = x; v = y;
+}
+// read_image<2> (:79-110): bilinear, clamped, position in [0,1]^2 scaled by (resolution - 1)
+__device__ __forceinline__ void read_image2(const float* __restrict__ data, int rw, int rh, float px, float py, float& ox, float& oy) {
+	const float fx = px * (float)(rw - 1), fy = py * (float)(rh - 1);
+	const int tx = (int)fx, ty = (int)fy;
+	const float wx = fx - (float)tx, wy = fy - (float)ty;
+	auto rd = [&](int x, int y) { x = max(min(x, rw - 1), 0); y = max(min(y, rh - 1), 0); return *reinterpret_cast<const float2*>(data + 2 * ((size_t)x + (size_t)y * rw)); };
+	const float2 a = rd(tx, ty), b = rd(tx + 1, ty), c = rd(tx, ty + 1), d = rd(tx + 1, ty + 1);
+	ox = (1.0f - wx) * (1.0f - wy) * a.x + wx * (1.0f - wy) * b.x + (1.0f - wx) * wy * c.x + wx * wy * d.x;
+	oy = (1.0f - wx) * (1.0f - wy) * a.y + wx * (1.0f - wy) * b.y + (1.0f - wx) * wy * c.y + wx * wy * d.y;
+}
+// read_envmap (envmap.cuh:30-62): latitude-longitude map, bilinear, wraps in x, clamps in y
+__device__ __forceinline__ float4 read_envmap(const float* __restrict__ data, int rw, int rh, V3 dir) {
+	// dir_to_spherical_unorm({dir.z, -dir.x, dir.y}) (random_val.cuh:64-69)
+	const float cos_theta = fminf(fmaxf(dir.y, -1.0f), 1.0f);
+	const float theta = acosf(cos_theta);
+	const float phi = atan2f(-dir.x, dir.z);
+	const float cyl_x = theta / 3.14159265358979323846f, cyl_y = phi / (2.0f * 3.14159265358979323846f) + 0.5f;
+	const float ex = cyl_y * (float)(rw - 1), ey = cyl_x * (float)(rh - 1);
+	const int tx = (int)ex, ty = (int)ey;
+	const float wx = ex - (float)tx, wy = ey - (float)ty;
+	auto rd = [&](int x, int y) {
+		if (x < 0) x += rw; else if (x >= rw) x -= rw;
+		y = max(min(y, rh - 1), 0);
+		return *reinterpret_cast<const float4*>(data + 4 * ((size_t)x + (size_t)y * rw));
+	};
+	const float4 a = rd(tx, ty), b = rd(tx + 1, ty), c = rd(tx, ty + 1), d = rd(tx + 1, ty + 1);
+	const float w00 = (1.0f - wx) * (1.0f - wy), w10 = wx * (1.0f - wy), w01 = (1.0f - wx) * wy, w11 = wx * wy;
+	return make_float4(w00 * a.x + w10 * b.x + w01 * c.x + w11 * d.x, w00 * a.y + w10 * b.y + w01 * c.y + w11 * d.y,
+	                   w00 * a.z + w10 * b.z + w01 * c.z + w11 * d.z, w00 * a.w + w10 * b.w + w01 * c.w + w11 * d.w);
+}
+// init_rays_with_payload_kernel_nerf (:2546-2595) with the general pixel_to_ray. r.o / r.d are valid even when the ray misses the AABB (the
+// environment map is looked up for every pixel).
+__device__ __forceinline__ bool make_ray_general(const DevFrame& f, uint32_t px, uint32_t py, Ray& r) {
+	const uint32_t idx = px + (uint32_t)f.W * py;
+	const float fw = (float)f.W, fh = (float)f.H;
+	const float u = ((float)px + 0.5f) * (1.0f / fw), v = ((float)py + 0.5f) * (1.0f / fh);
+	const float rt = f.rs[0] + f.rs[1] * u + f.rs[2] * v + f.rs[3] * ld_random_val(f.spp, idx * 72239731u);
+	float cam[12];
+#pragma unroll
+	for (int i = 0; i < 12; ++i) cam[i] = f.cam0[i] * rt + f.cam1[i] * (1.0f - rt);
+	const float uvx = ((float)px + f.pix_off[0]) / fw, uvy = ((float)py + f.pix_off[1]) / fh;
+	V3 dl;
+	if (f.cam_dist_mode == 2) {  // f_theta_undistortion (:232-245)
+		const float xpix = (uvx - f.cx) * f.cam_dist[5], ypix = (uvy - f.cy) * f.cam_dist[6];
+		const float norm = sqrtf(xpix * xpix + ypix * ypix);
+		const float alpha = f.cam_dist[0] + norm * (f.cam_dist[1] + norm * (f.cam_dist[2] + norm * (f.cam_dist[3] + norm * f.cam_dist[4])));
+		float sa, ca;
+		sincosf(alpha, &sa, &ca);
+		if (ca <= 1.17549435e-38f || norm == 0.0f) {  // the reference returns a ray outside the AABB: the pixel is not rendered
+			r.o = v3(1000.0f, 0.0f, 0.0f);
+			r.d = v3(0.0f, 0.0f, 1.0f);
+			return false;
+		}
+		sa *= 1.0f / norm;
+		dl = v3(sa * xpix, sa * ypix, ca);
+	} else {
+		dl = v3((uvx - f.cx) * fw / f.fx, (uvy - f.cy) * fh / f.fy, 1.0f);
+		if (f.cam_dist_mode == 1) iterative_camera_undistortion(f.cam_dist, dl.x, dl.y);
+	}
+	if (f.distortion) {
+		float ox, oy;
+		read_image2(f.distortion, f.dist_w, f.dist_h, uvx, uvy, ox, oy);
+		dl.x += ox; dl.y += oy;
+	}
+	V3 d = matvec3(cam, dl);
+	V3 o = v3(cam[9], cam[10], cam[11]);
+	if (f.dof != 0.0f) {
+		const V3 lookat = v3(o.x + d.x * f.focus_z, o.y + d.y * f.focus_z, o.z + d.z * f.focus_z);
+		float sx, sy;
+		ld_random_val_2d(f.spp, px * 19349663u + py * 96925573u, sx, sy);
+		const float a = sx * 2.0f - 1.0f, b = sy * 2.0f - 1.0f;  // square2disk_shirley
+		float rr, phi;
+		if (a * a > b * b) { rr = a; phi = (3.14159265358979323846f / 4.0f) * (b / a); }
+		else { rr = b; phi = (3.14159265358979323846f / 2.0f) - (3.14159265358979323846f / 4.0f) * (a / b); }
+		float sp, cp;
+		sincosf(phi, &sp, &cp);
+		const float bx = f.dof * (rr * cp), by = f.dof * (rr * sp);
+		o = v3(o.x + (cam[0] * bx + cam[3] * by), o.y + (cam[1] * bx + cam[4] * by), o.z + (cam[2] * bx + cam[5] * by));
+		d = v3((lookat.x - o.x) / f.focus_z, (lookat.y - o.y) / f.focus_z, (lookat.z - o.z) / f.focus_z);
+	}
+	const float n2 = d.x * d.x + d.y * d.y + d.z * d.z;
+	if (n2 > 0.0f) { const float n = sqrtf(n2); d = v3(d.x / n, d.y / n, d.z / n); }
+	r.o = o;
+	r.d = d;
+	const float t = add(fmaxf(box_ray_tmin(f.rmin, f.rmax, o, d), 0.05f), 1e-6f);
+	if (!box_contains(f.rmin, f.rmax, madd3(d, t, o))) return false;
+	r.t = t;
+	return true;
+}
+
+// glow_mode of composite_kernel_nerf (:807-903): grid-line visualisation added to (or replacing) a sample's colour; `weight_mask` multiplies the
+// sample's weight (mask_to_alpha). pos = the sample's unwarped position, cam_origin = camera_matrix.col(3). Everything by value (an array
+// passed by address would move the caller's colour into local memory on the hot path): returns {r, g, b, weight mask}.
+__device__ __noinline__ float4 glow_apply(int glow_mode, float glow_y_cutoff, V3 pos, V3 cam_origin, float r_in, float g_in, float b_in) {
+	float rgb[3] = {r_in, g_in, b_in};
+	float weight_mask = 1.0f;
+	float glow = 0.0f;
+	const bool green_grid = glow_mode & 1, green_cutline = glow_mode & 2, mask_to_alpha = glow_mode & 4, radial_mode = glow_mode & 8, grid_mode = glow_mode & 16;
+	float dist;
+	if (radial_mode) {
+		const V3 q = vsub(pos, cam_origin);
+		dist = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+		dist = fminf(dist, (4.5f - pos.y) * 0.333f);
+	} else {
+		dist = pos.y;
+	}
+	if (grid_mode) {
+		glow = 1.0f / fmaxf(1.0f, dist);
+	} else {
+		float y = glow_y_cutoff - dist;
+		float mask = 0.0f;
+		if (y > 0.0f) {
+			y *= 80.0f;
+			mask = fminf(1.0f, y);
+			if (green_cutline) glow += fmaxf(0.0f, 1.0f - fabsf(1.0f - y)) * 4.0f;
+			if (y > 1.0f) y = 1.0f - (y - 1.0f) * 0.05f;
+			if (green_grid) glow += fmaxf(0.0f, y / fmaxf(1.0f, dist));
+		}
+		if (mask_to_alpha) weight_mask = mask;
+	}
+	if (glow > 0.0f) {
+		float line = 0.0f;
+		const float pi = 3.141592653589793f;
+#pragma unroll 1
+		for (int k = 0; k < 4; ++k) {
+			const float m = (float)(2 << k);  // 2, 4, 8, 16
+			line += fmaxf(0.0f, cosf(pos.y * m * pi * 16.0f) - 0.975f);
+			line += fmaxf(0.0f, cosf(pos.x * m * pi * 16.0f) - 0.975f);
+			line += fmaxf(0.0f, cosf(pos.z * m * pi * 16.0f) - 0.975f);
+		}
+		if (grid_mode) {
+			glow = glow * line * 15.0f;
+			rgb[1] = glow; rgb[2] = glow * 0.5f; rgb[0] = glow * 0.25f;
+		} else {
+			glow = glow * glow * 0.25f + glow * line * 15.0f;
+			rgb[1] += glow; rgb[2] += glow * 0.5f; rgb[0] += glow * 0.25f;
+		}
+	}
+	return make_float4(rgb[0], rgb[1], rgb[2], weight_mask);
 }
 
 // Next occupied sample at or after t. false: the ray left the render AABB.

@@ -47,13 +47,18 @@ __device__ __forceinline__ bool tile_pixel(const DevFrame& f, uint32_t tile, uin
 // of compact_kernel_nerf (:2485), with warp-aggregated atomics instead of one global atomic per ray.
 // The long empty-space walk to a ray's first occupied sample is a serial chain of dependent occupancy loads;
 // here it is hidden by running every ray of the frame concurrently instead of stalling an MLP round.
-__global__ void __launch_bounds__(256) k_prepare_rays(const DevFrame f, const uint8_t* __restrict__ bitfield, float* __restrict__ depth_out,
-                                                      RayRec* __restrict__ list, uint32_t* __restrict__ n_queued, uint32_t n_local_pixels,
+// GENERAL: frames with lens distortion / a distortion map / depth of field (f.general_camera), an environment map or the Distortion render mode.
+// Their rays cost a Newton iteration or a sincosf to generate, so the queued ones are handed to the persistent renderer in `ray_od` (origin and
+// direction, 6 floats per queue slot) instead of being re-derived from the pixel index there; the common pinhole path stays as lean as it was.
+template <bool GENERAL>
+__global__ void __launch_bounds__(256) k_prepare_rays(const DevFrame f, const uint8_t* __restrict__ bitfield, float4* __restrict__ fb, float* __restrict__ depth_out,
+                                                      RayRec* __restrict__ list, float* __restrict__ ray_od, uint32_t* __restrict__ n_queued, uint32_t n_local_pixels,
                                                       unsigned long long* __restrict__ stats) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool queued = false, is_ray = false, entered = false;
 	uint32_t pix = 0;
 	float t = 0.0f;
+	Ray r;
 	if (i < n_local_pixels) {
 		uint32_t tile = (uint32_t)f.tile_rank + (i / (uint32_t)TILE_PIXELS) * (uint32_t)f.tile_world;
 		uint32_t px, py;
@@ -61,8 +66,24 @@ __global__ void __launch_bounds__(256) k_prepare_rays(const DevFrame f, const ui
 			is_ray = true;
 			pix = px + (uint32_t)f.W * py;
 			depth_out[pix] = 1e10f;  // :2581
-			Ray r;
-			if (make_ray(f, px, py, r)) {
+			bool inside;
+			if constexpr (GENERAL) {
+				inside = f.general_camera ? make_ray_general(f, px, py, r) : make_ray(f, px, py, r);
+				if (f.envmap) fb[pix] = read_envmap(f.envmap, f.env_w, f.env_h, r.d);  // every pixel, before the AABB test (:2581-2583)
+				if (inside && f.mode == NSB_RENDER_DISTORTION) {  // :2596-2607: the map itself, written by ray initialisation; the ray is not traced
+					float dx = 0.5f, dy = 0.5f;
+					if (f.distortion) {
+						read_image2(f.distortion, f.dist_w, f.dist_h, ((float)px + 0.5f) / (float)f.W, ((float)py + 0.5f) / (float)f.H, dx, dy);
+						dx = dx * 50.0f + 0.5f; dy = dy * 50.0f + 0.5f;
+					}
+					fb[pix] = make_float4(dx, dy, 0.5f, 1.0f);
+					depth_out[pix] = 1.0f;
+					inside = false;
+				}
+			} else {
+				inside = make_ray(f, px, py, r);
+			}
+			if (inside) {
 				entered = true;
 				V3 idir = v3(div_(1.0f, r.d.x), div_(1.0f, r.d.y), div_(1.0f, r.d.z));
 				t = fma_(ld_random_val(f.spp, pix * 786433u), calc_dt(r.t, f.cone), r.t);  // advance_pos_nerf :585
@@ -85,7 +106,14 @@ __global__ void __launch_bounds__(256) k_prepare_rays(const DevFrame f, const ui
 		RayRec rr;
 		rr.pix = pix;
 		rr.t = t;
-		list[base + __popc(m & ((1u << lane) - 1u))] = rr;
+		const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+		list[slot] = rr;
+		if constexpr (GENERAL) {
+			if (ray_od) {
+				float* od = ray_od + 6 * (size_t)slot;
+				od[0] = r.o.x; od[1] = r.o.y; od[2] = r.o.z; od[3] = r.d.x; od[4] = r.d.y; od[5] = r.d.z;
+			}
+		}
 	}
 }
 
@@ -170,7 +198,7 @@ template <bool OPS, bool ACC16>
 __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
                                                       float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
-                                                      const uint32_t* __restrict__ n_queued_ptr, uint32_t* fetch_counter,
+                                                      const float* __restrict__ ray_od, const uint32_t* __restrict__ n_queued_ptr, uint32_t* fetch_counter,
                                                       unsigned long long* __restrict__ stats, const int refill_thr, const int dda_flags) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
 	RenderSmem& RS = *reinterpret_cast<RenderSmem*>(smem_raw);
@@ -213,7 +241,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	// reference's own n_steps > 1 batching; frames are bit-identical with or without helpers. help_mode 1: only once the queue is exhausted, 2: always.
 	// MEASURED (profiles/README.md, round 2): 13.5 % fewer rounds but each round 27 % dearer — the loop's cost follows the samples evaluated (gather
 	// wavefronts + issue), not the rounds — so the default is 0 and this stays an opt-in experiment.
-	const int help_mode = OPS ? 0 : (dda_flags >> 16) & 3;  // host: NSB_HELPERS
+	const int help_mode = (OPS || (f.glow_mode & 4)) ? 0 : (dda_flags >> 16) & 3;  // host: NSB_HELPERS (the mailbox does not carry glow's weight mask)
 	constexpr uint32_t HELP_DEPTH = 7;
 	// mailbox helper -> owner: the tile's A-operand buffer is idle between the last MMA of a round and the next encode, and every warp only ever
 	// writes its own 32 rows of it: field q of lane l lives in k-chunk q, at this warp's 512 bytes
@@ -304,9 +332,14 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 					if (qi != 0xffffffffu) {
 						const RayRec rr = list[qi];
 						pix = rr.pix;
-						Ray r;
-						make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
-						ro = r.o; rd = r.d;
+						if (ray_od) {  // a general-camera frame: k_prepare_rays<true> left the ray next to its queue entry
+							const float* od = ray_od + 6 * (size_t)qi;
+							ro = v3(od[0], od[1], od[2]); rd = v3(od[3], od[4], od[5]);
+						} else {
+							Ray r;
+							make_ray(f, pix % (uint32_t)f.W, pix / (uint32_t)f.W, r);
+							ro = r.o; rd = r.d;
+						}
 						t = rr.t;
 						TB.ray[R_OX][tid] = ro.x; TB.ray[R_OY][tid] = ro.y; TB.ray[R_OZ][tid] = ro.z;
 						TB.ray[R_DX][tid] = rd.x; TB.ray[R_DY][tid] = rd.y; TB.ray[R_DZ][tid] = rd.z;
@@ -429,6 +462,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 
 		// ---- composite_kernel_nerf :750-955, split in two: what depends on the sample alone (any lane), then the ray's running sums (its owner lane) ----
 		float s_alpha = 0.0f, s_e[3] = {0.0f, 0.0f, 0.0f}, s_z = 0.0f;
+		float s_mask = 1.0f;  // glow_mode's mask_to_alpha: multiplies the sample's weight (:877-879)
 		if (has_sample) {
 			const uint32_t rtid = h_owner < 0 ? tid : (tid & ~31u) + (uint32_t)h_owner;  // the slot of the ray this sample belongs to
 			const V3 cam_fwd = v3(f.cam1[6], f.cam1[7], f.cam1[8]);
@@ -453,6 +487,10 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 			}
 			if (f.show_accel) alpha = 1.0f;  // show_accel >= 0: the occupancy cells themselves are drawn (:788-790)
 			float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
+			if (f.glow_mode) {  // :807-903, before the mode overrides
+				const float4 gl = glow_apply(f.glow_mode, f.glow_y_cutoff, cpos, v3(f.cam1[9], f.cam1[10], f.cam1[11]), rgb[0], rgb[1], rgb[2]);
+				rgb[0] = gl.x; rgb[1] = gl.y; rgb[2] = gl.z; s_mask = gl.w;
+			}
 			if (f.mode != NSB_RENDER_SHADE) {
 				const V3 ro = v3(TB.ray[R_OX][rtid], TB.ray[R_OY][rtid], TB.ray[R_OZ][rtid]);
 				if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
@@ -517,7 +555,24 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 					finish(false, cr, cg, cb, ca, ray_depth);
 				}
 			};
-			accumulate(s_alpha, s_e[0], s_e[1], s_e[2], s_z);
+			if (f.glow_mode & 4) {
+				// mask_to_alpha: weight *= mask (a separate copy so that the unmasked expression — and its FMA contraction — stays exactly the reference's)
+				float T = 1.0f - ca;
+				float weight = s_alpha * T;
+				weight *= s_mask;
+				cr = __fmaf_rn(s_e[0], weight, cr);
+				cg = __fmaf_rn(s_e[1], weight, cg);
+				cb = __fmaf_rn(s_e[2], weight, cb);
+				ca += weight;
+				if (weight > max_weight) { max_weight = weight; ray_depth = s_z; }
+				if (ca > sat) {
+					float a = ca;
+					cr = __fdiv_rn(cr, a); cg = __fdiv_rn(cg, a); cb = __fdiv_rn(cb, a); ca = __fdiv_rn(ca, a);
+					finish(false, cr, cg, cb, ca, ray_depth);
+				}
+			} else {
+				accumulate(s_alpha, s_e[0], s_e[1], s_e[2], s_z);
+			}
 			if constexpr (!OPS) {
 				if (h_free && h_per_ray) {  // this ray's helpers: consecutive free lanes from free-rank h_first, in march order
 					const float* wbox = mbox - lane;
@@ -715,6 +770,7 @@ __global__ void k_poisson_residual_density(const DevOp* __restrict__ ops, int n_
 	}
 }
 
+template <bool GENERAL>
 __global__ void k_march_trace(const DevFrame f, const uint8_t* __restrict__ bitfield, const uint32_t* __restrict__ pixels, uint32_t n_pixels,
                               uint32_t max_samples, float* __restrict__ rec, uint32_t* __restrict__ idx, uint32_t* __restrict__ count) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -723,7 +779,7 @@ __global__ void k_march_trace(const DevFrame f, const uint8_t* __restrict__ bitf
 	uint32_t px = pix % (uint32_t)f.W, py = pix / (uint32_t)f.W;
 	Ray r;
 	uint32_t c = 0;
-	if (make_ray(f, px, py, r)) {
+	if (GENERAL ? make_ray_general(f, px, py, r) : make_ray(f, px, py, r)) {
 		V3 idir = v3(div_(1.0f, r.d.x), div_(1.0f, r.d.y), div_(1.0f, r.d.z));
 		float t = fma_(ld_random_val(f.spp, pix * 786433u), calc_dt(r.t, f.cone), r.t);
 		while (c < MARCH_ITER) {
@@ -1038,6 +1094,8 @@ struct NsbContext {
 	unsigned long long* d_stats = nullptr;
 	RayRec* d_list = nullptr;
 	size_t list_capacity = 0;
+	float* d_ray_od = nullptr;     // origin + direction per queue slot, general-camera frames only (allocated on the first such frame)
+	size_t ray_od_capacity = 0;
 	int acc16 = 1;                 // MLP accumulator policy: 1 fp16 TMEM accumulators (default: the reference's wmma __half fragments), 0 fp32 (nsb_set_mlp_accumulator)
 	int use_ws = 0;                // NSB_WS=1: frames without operators go through the warp-specialised kernel (experimental; default k_render_fused<false>)
 	int helpers = 0;               // helper lanes of k_render_fused (frames without operators; experiment, measured slower: profiles/README.md): 0 off (default), 1 once the queue is exhausted, 2 always (NSB_HELPERS)
@@ -1194,7 +1252,7 @@ extern "C" NsbStatus nsb_destroy(NsbContext* c) {
 	free_ops(c);
 	cudaFree(c->d_grid); cudaFree(c->d_wimage); cudaFree(c->d_wrow); cudaFree(c->d_bitfield);
 	cudaFree(c->d_density_grid); cudaFree(c->d_density_tmp); cudaFree(c->d_mean_partial); cudaFree(c->d_thresh);
-	cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_fb); cudaFree(c->d_depth); cudaFree(c->d_list);
+	cudaFree(c->d_counters); cudaFree(c->d_stats); cudaFree(c->d_fb); cudaFree(c->d_depth); cudaFree(c->d_list); cudaFree(c->d_ray_od);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->evm) cudaEventDestroy(c->evm);
@@ -1727,9 +1785,14 @@ static NsbStatus to_dev_frame(const NsbFrame* f, DevFrame* d) {
 	if (f->tile_world <= 0 || f->tile_rank < 0 || f->tile_rank >= f->tile_world) return fail(NSB_ERR_INVALID, "bad tile partition %d/%d", f->tile_rank, f->tile_world);
 	switch (f->render_mode) {
 		case NSB_RENDER_AO: case NSB_RENDER_SHADE: case NSB_RENDER_POSITIONS: case NSB_RENDER_DEPTH:
-		case NSB_RENDER_DISTANCE: case NSB_RENDER_STEPSIZE: case NSB_RENDER_COST: break;
-		default: return fail(NSB_ERR_UNSUPPORTED, "render mode %d is not covered (Normals/EncodingVis need network input gradients; Slice/Distortion are side paths)", f->render_mode);
+		case NSB_RENDER_DISTANCE: case NSB_RENDER_STEPSIZE: case NSB_RENDER_COST: case NSB_RENDER_DISTORTION: break;
+		default: return fail(NSB_ERR_UNSUPPORTED, "render mode %d is not covered (Normals/EncodingVis need network input gradients; Slice is a side path)", f->render_mode);
 	}
+	if (f->camera_distortion_mode < 0 || f->camera_distortion_mode > 2) return fail(NSB_ERR_INVALID, "bad camera distortion mode %d", f->camera_distortion_mode);
+	if (f->focus_z < 0.0f) return fail(NSB_ERR_UNSUPPORTED, "negative focus_z selects the reference's Slice side path (testbed_nerf.cu:3067-3070), which is not covered");
+	if (f->dof != 0.0f && !(f->focus_z > 0.0f)) return fail(NSB_ERR_INVALID, "depth of field needs focus_z > 0");
+	if (f->envmap_dev && (f->envmap_resolution[0] <= 0 || f->envmap_resolution[1] <= 0)) return fail(NSB_ERR_INVALID, "bad envmap resolution");
+	if (f->distortion_dev && (f->distortion_resolution[0] <= 0 || f->distortion_resolution[1] <= 0)) return fail(NSB_ERR_INVALID, "bad distortion map resolution");
 	if (f->rgb_activation < 0 || f->rgb_activation > 3 || f->density_activation < 0 || f->density_activation > 3) return fail(NSB_ERR_INVALID, "bad activation");
 	d->W = f->width; d->H = f->height;
 	d->fx = f->focal_length[0]; d->fy = f->focal_length[1];
@@ -1751,6 +1814,13 @@ static NsbStatus to_dev_frame(const NsbFrame* f, DevFrame* d) {
 	d->tile_rank = f->tile_rank; d->tile_world = f->tile_world;
 	d->tiles_x = (f->width + TILE_W - 1) / TILE_W;
 	d->tiles_y = (f->height + TILE_H - 1) / TILE_H;
+	d->cam_dist_mode = f->camera_distortion_mode;
+	memcpy(d->cam_dist, f->camera_distortion_params, sizeof(d->cam_dist));
+	d->dof = f->dof; d->focus_z = f->focus_z;
+	d->glow_mode = f->glow_mode; d->glow_y_cutoff = f->glow_y_cutoff;
+	d->envmap = f->envmap_dev; d->env_w = f->envmap_resolution[0]; d->env_h = f->envmap_resolution[1];
+	d->distortion = f->distortion_dev; d->dist_w = f->distortion_resolution[0]; d->dist_h = f->distortion_resolution[1];
+	d->general_camera = (d->cam_dist_mode != 0 || d->distortion != nullptr || d->dof != 0.0f) ? 1 : 0;
 	return NSB_OK;
 }
 
@@ -1772,19 +1842,36 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		CU(cudaMalloc(&c->d_list, n_local * sizeof(RayRec)));
 		c->list_capacity = n_local;
 	}
+	// frames whose ray generation is not the pinhole fast path (ABI 3): k_prepare_rays<true>; with a general camera the rays travel in a side buffer
+	const bool general = f.general_camera || f.envmap != nullptr || f.mode == NSB_RENDER_DISTORTION;
+	float* ray_od = nullptr;
+	if (f.general_camera) {
+		if (n_local > c->ray_od_capacity) {
+			CU(cudaStreamSynchronize(stream));
+			cudaFree(c->d_ray_od);
+			c->d_ray_od = nullptr; c->ray_od_capacity = 0;
+			CU(cudaMalloc(&c->d_ray_od, n_local * 6 * sizeof(float)));
+			c->ray_od_capacity = n_local;
+		}
+		ray_od = c->d_ray_od;
+	}
 	CU(cudaEventRecord(c->ev0, stream));
 	CU(cudaEventRecord(c->evm, stream));
 	CU(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(uint32_t), stream));
 	CU(cudaMemsetAsync(c->d_stats, 0, ST_N * sizeof(unsigned long long), stream));
 	if (n_local > 0) {
-		k_prepare_rays<<<(unsigned)((n_local + 255) / 256), 256, 0, stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, depth_dev, c->d_list, c->d_counters,
-		                                                                   (uint32_t)n_local, c->d_stats);
+		if (general)
+			k_prepare_rays<true><<<(unsigned)((n_local + 255) / 256), 256, 0, stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list,
+			                                                                         ray_od, c->d_counters, (uint32_t)n_local, c->d_stats);
+		else
+			k_prepare_rays<false><<<(unsigned)((n_local + 255) / 256), 256, 0, stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list,
+			                                                                          nullptr, c->d_counters, (uint32_t)n_local, c->d_stats);
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(c->evm, stream));
 		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
 		if (grid > (my_tiles + NSB_TILES - 1) / NSB_TILES) grid = (uint32_t)((my_tiles + NSB_TILES - 1) / NSB_TILES);
 		const bool ops_on = f.apply_ops && c->n_ops > 0;
-		if (!ops_on && c->use_ws && !c->acc16 && !f.show_accel && (uint64_t)f.W * (uint64_t)f.H < (1ull << 28)) {  // k_render_ws ships the pixel in 28 bits of a flag word
+		if (!ops_on && c->use_ws && !c->acc16 && !f.show_accel && !f.general_camera && !f.glow_mode && (uint64_t)f.W * (uint64_t)f.H < (1ull << 28)) {  // k_render_ws ships the pixel in 28 bits of a flag word
 			uint32_t g2 = (uint32_t)c->sm_count;
 			if (g2 > (my_tiles + ws::PT - 1) / ws::PT) g2 = (uint32_t)((my_tiles + ws::PT - 1) / ws::PT);
 			k_render_ws<<<g2, ws::THREADS, sizeof(ws::Smem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list,
@@ -1792,7 +1879,7 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 		} else {
 		auto kernel = ops_on ? (c->acc16 ? k_render_fused<true, true> : k_render_fused<true, false>) : (c->acc16 ? k_render_fused<false, true> : k_render_fused<false, false>);
 		kernel<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
-		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, c->d_counters, c->d_counters + 1, c->d_stats,
+		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, ray_od, c->d_counters, c->d_counters + 1, c->d_stats,
 		                                                          c->refill_thr, c->dda_budget | (c->helpers << 16));
 		}
 		CU(cudaGetLastError());
@@ -2028,7 +2115,8 @@ extern "C" NsbStatus nsb_march_trace(NsbContext* c, const NsbFrame* frame, const
 	if (st != NSB_OK) return st;
 	if (n_pixels == 0) return NSB_OK;
 	CU(cudaSetDevice(c->device));
-	k_march_trace<<<(n_pixels + 63) / 64, 64, 0, (cudaStream_t)stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, pixels, n_pixels, max_samples, rec, idx, count);
+	if (f.general_camera) k_march_trace<true><<<(n_pixels + 63) / 64, 64, 0, (cudaStream_t)stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, pixels, n_pixels, max_samples, rec, idx, count);
+	else k_march_trace<false><<<(n_pixels + 63) / 64, 64, 0, (cudaStream_t)stream>>>(f, c->has_occ ? c->d_bitfield : nullptr, pixels, n_pixels, max_samples, rec, idx, count);
 	CU(cudaGetLastError());
 	return NSB_OK;
 }

@@ -327,3 +327,48 @@ def make_frame(model: SyntheticModel, camera: np.ndarray, width: int = 1920, hei
     f.min_mip = 0
     f.tile_rank, f.tile_world = rank, world
     return f
+
+
+# ---------------------------------------------------------------------------------------------
+# ABI 3 frame extras: lens distortion, depth of field, glow, environment and distortion maps
+# ---------------------------------------------------------------------------------------------
+def make_envmap(width: int = 64, height: int = 32, seed: int = 11) -> np.ndarray:
+    """A smooth latitude-longitude RGBA map [height, width, 4] (float32, alpha 1): what m_envmap holds (envmap.cuh:30-62)."""
+    rng = np.random.default_rng(seed)
+    u = np.linspace(0.0, 2.0 * np.pi, width, endpoint=False, dtype=np.float32)[None, :]
+    v = np.linspace(0.0, np.pi, height, dtype=np.float32)[:, None]
+    out = np.ones((height, width, 4), np.float32)
+    for c in range(3):
+        a, b, p = rng.uniform(0.1, 0.4, 3).astype(np.float32)
+        out[..., c] = 0.5 + a * np.cos((c + 1) * u + p) * np.sin(v) + b * np.cos(2.0 * v + p)
+    return np.ascontiguousarray(out)
+
+
+def make_distortion_map(width: int = 32, height: int = 18, amplitude: float = 0.01, seed: int = 12) -> np.ndarray:
+    """A smooth per-pixel offset of the camera-space ray direction [height, width, 2] (m_distortion.map, pixel_to_ray :278-280)."""
+    rng = np.random.default_rng(seed)
+    x = np.linspace(0.0, 1.0, width, dtype=np.float32)[None, :]
+    y = np.linspace(0.0, 1.0, height, dtype=np.float32)[:, None]
+    p = rng.uniform(0.0, np.pi, 4).astype(np.float32)
+    out = np.zeros((height, width, 2), np.float32)
+    out[..., 0] = amplitude * np.sin(2.0 * np.pi * x + p[0]) * np.cos(np.pi * y + p[1])
+    out[..., 1] = amplitude * np.cos(np.pi * x + p[2]) * np.sin(2.0 * np.pi * y + p[3])
+    return np.ascontiguousarray(out)
+
+
+def set_camera_distortion(f: abi.NsbFrame, mode: int, params) -> abi.NsbFrame:
+    f.camera_distortion_mode = mode
+    for i in range(7):
+        f.camera_distortion_params[i] = float(params[i]) if i < len(params) else 0.0
+    return f
+
+
+def set_maps(f: abi.NsbFrame, envmap_ptr: int = 0, envmap_shape=None, distortion_ptr: int = 0, distortion_shape=None) -> abi.NsbFrame:
+    """Pointers are what the consumer can read: device pointers for nsb_render, host pointers for a CPU consumer (the tests' checker)."""
+    f.envmap_dev = envmap_ptr or None
+    if envmap_shape is not None:
+        f.envmap_resolution[0], f.envmap_resolution[1] = int(envmap_shape[1]), int(envmap_shape[0])
+    f.distortion_dev = distortion_ptr or None
+    if distortion_shape is not None:
+        f.distortion_resolution[0], f.distortion_resolution[1] = int(distortion_shape[1]), int(distortion_shape[0])
+    return f

@@ -623,7 +623,183 @@ void poisson_one(const NsbEditOp* ops, int n_ops, V3 pos_w, float* sh27, float* 
 // ----------------------------------------------------------------------------------------
 struct Ray { V3 o, d; float t; bool alive; };
 
+// ---- the general camera (ABI 3): pixel_to_ray with lens distortion, distortion map, depth of field (common_device.cuh:79-110,145-295),
+// ld_random_val_2d / square2disk_shirley (random_val.cuh:109-127,278-282), read_envmap (envmap.cuh:30-62). Held to the frame tolerance, not bit-pinned.
+static void apply_camera_distortion(const float* p, float u, float v, float& du, float& dv) {  // :145-160
+	const float k1 = p[0], k2 = p[1], p1 = p[2], p2 = p[3];
+	const float u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2;
+	const float radial = k1 * r2 + k2 * r2 * r2;
+	du = u * radial + 2.0f * p1 * uv + p2 * (r2 + 2.0f * u2);
+	dv = v * radial + 2.0f * p2 * uv + p1 * (r2 + 2.0f * v2);
+}
+static void iterative_camera_undistortion(const float* params, float& u, float& v) {  // :163-197
+	const float x0 = u, y0 = v;
+	float x = u, y = v;
+	for (uint32_t i = 0; i < 100u; ++i) {
+		const float step0 = fmaxf(1.1920928955078125e-7f, fabsf(1e-6f * x));
+		const float step1 = fmaxf(1.1920928955078125e-7f, fabsf(1e-6f * y));
+		float dx, dy, dx0b, dy0b, dx0f, dy0f, dx1b, dy1b, dx1f, dy1f;
+		apply_camera_distortion(params, x, y, dx, dy);
+		apply_camera_distortion(params, x - step0, y, dx0b, dy0b);
+		apply_camera_distortion(params, x + step0, y, dx0f, dy0f);
+		apply_camera_distortion(params, x, y - step1, dx1b, dy1b);
+		apply_camera_distortion(params, x, y + step1, dx1f, dy1f);
+		const float j00 = 1.0f + (dx0f - dx0b) / (2.0f * step0), j01 = (dx1f - dx1b) / (2.0f * step1);
+		const float j10 = (dy0f - dy0b) / (2.0f * step0), j11 = 1.0f + (dy1f - dy1b) / (2.0f * step1);
+		const float rx = x + dx - x0, ry = y + dy - y0;
+		const float invdet = 1.0f / (j00 * j11 - j10 * j01);  // Eigen's 2x2 inverse: adjugate times 1/det
+		const float sx = (j11 * invdet) * rx + (-j01 * invdet) * ry;
+		const float sy = (-j10 * invdet) * rx + (j00 * invdet) * ry;
+		x -= sx; y -= sy;
+		if (sx * sx + sy * sy < 1e-10f) break;
+	}
+	u = x; v = y;
+}
+static const uint32_t kSobolDir1[32] = {
+	0x80000000u, 0xc0000000u, 0xa0000000u, 0xf0000000u, 0x88000000u, 0xcc000000u, 0xaa000000u, 0xff000000u, 0x80800000u, 0xc0c00000u, 0xa0a00000u,
+	0xf0f00000u, 0x88880000u, 0xcccc0000u, 0xaaaa0000u, 0xffff0000u, 0x80008000u, 0xc000c000u, 0xa000a000u, 0xf000f000u, 0x88008800u, 0xcc00cc00u,
+	0xaa00aa00u, 0xff00ff00u, 0x80808080u, 0xc0c0c0c0u, 0xa0a0a0a0u, 0xf0f0f0f0u, 0x88888888u, 0xccccccccu, 0xaaaaaaaau, 0xffffffffu,
+};
+static void ld_random_val_2d_general(uint32_t index, uint32_t seed, float& x, float& y) {
+	index = nested_uniform_scramble_base2(index, seed);
+	uint32_t X1 = 0;
+	for (uint32_t bit = 0; bit < 32; ++bit) X1 ^= ((index >> bit) & 1u) * kSobolDir1[bit];
+	x = (float)nested_uniform_scramble_base2(reverse_bits(index), hash_combine(seed, 0)) * 2.3283064365386963e-10f;
+	y = (float)nested_uniform_scramble_base2(X1, hash_combine(seed, 1)) * 2.3283064365386963e-10f;
+}
+static void read_image2(const float* data, int rw, int rh, float px, float py, float& ox, float& oy) {  // read_image<2> :79-110
+	const float fx = px * (float)(rw - 1), fy = py * (float)(rh - 1);
+	const int tx = (int)fx, ty = (int)fy;
+	const float wx = fx - (float)tx, wy = fy - (float)ty;
+	auto rd = [&](int x, int y, int c) { x = std::max(std::min(x, rw - 1), 0); y = std::max(std::min(y, rh - 1), 0); return data[2 * ((size_t)x + (size_t)y * rw) + c]; };
+	ox = (1.0f - wx) * (1.0f - wy) * rd(tx, ty, 0) + wx * (1.0f - wy) * rd(tx + 1, ty, 0) + (1.0f - wx) * wy * rd(tx, ty + 1, 0) + wx * wy * rd(tx + 1, ty + 1, 0);
+	oy = (1.0f - wx) * (1.0f - wy) * rd(tx, ty, 1) + wx * (1.0f - wy) * rd(tx + 1, ty, 1) + (1.0f - wx) * wy * rd(tx, ty + 1, 1) + wx * wy * rd(tx + 1, ty + 1, 1);
+}
+static void read_envmap(const float* data, int rw, int rh, V3 dir, float* out4) {  // envmap.cuh:30-62 over dir_to_spherical_unorm (random_val.cuh:64-69)
+	const float cos_theta = fminf(fmaxf(dir.y, -1.0f), 1.0f);
+	const float theta = acosf(cos_theta);
+	const float phi = atan2f(-dir.x, dir.z);
+	const float cyl_x = theta / 3.14159265358979323846f, cyl_y = phi / (2.0f * 3.14159265358979323846f) + 0.5f;
+	const float ex = cyl_y * (float)(rw - 1), ey = cyl_x * (float)(rh - 1);
+	const int tx = (int)ex, ty = (int)ey;
+	const float wx = ex - (float)tx, wy = ey - (float)ty;
+	auto rd = [&](int x, int y) {
+		if (x < 0) x += rw; else if (x >= rw) x -= rw;
+		y = std::max(std::min(y, rh - 1), 0);
+		return data + 4 * ((size_t)x + (size_t)y * rw);
+	};
+	const float *a = rd(tx, ty), *b = rd(tx + 1, ty), *c = rd(tx, ty + 1), *d = rd(tx + 1, ty + 1);
+	const float w00 = (1.0f - wx) * (1.0f - wy), w10 = wx * (1.0f - wy), w01 = (1.0f - wx) * wy, w11 = wx * wy;
+	for (int k = 0; k < 4; ++k) out4[k] = w00 * a[k] + w10 * b[k] + w01 * c[k] + w11 * d[k];
+}
+static bool general_camera(const NsbFrame& f) { return f.camera_distortion_mode != 0 || f.distortion_dev != nullptr || f.dof != 0.0f; }
+
+Ray make_ray_general(const NsbFrame& f, uint32_t px, uint32_t py) {
+	Ray r;
+	r.alive = false;
+	const uint32_t W = (uint32_t)f.width, H = (uint32_t)f.height, idx = px + W * py;
+	const float fw = (float)W, fh = (float)H;
+	const float u = ((float)px + 0.5f) * (1.0f / fw), v = ((float)py + 0.5f) * (1.0f / fh);
+	const float rt = f.rolling_shutter[0] + f.rolling_shutter[1] * u + f.rolling_shutter[2] * v + f.rolling_shutter[3] * ld_random_val(f.spp_index, idx * 72239731u);
+	float cam[12];
+	for (int i = 0; i < 12; ++i) cam[i] = f.camera0[i] * rt + f.camera1[i] * (1.0f - rt);
+	float off[2];
+	ld_random_pixel_offset(f.snap_to_pixel_centers ? 0u : f.spp_index, off);
+	const float uvx = ((float)px + off[0]) / fw, uvy = ((float)py + off[1]) / fh;
+	const float* cd = f.camera_distortion_params;
+	V3 dl;
+	if (f.camera_distortion_mode == 2) {  // f_theta_undistortion (:232-245)
+		const float xpix = (uvx - f.screen_center[0]) * cd[5], ypix = (uvy - f.screen_center[1]) * cd[6];
+		const float norm = sqrtf(xpix * xpix + ypix * ypix);
+		const float alpha = cd[0] + norm * (cd[1] + norm * (cd[2] + norm * (cd[3] + norm * cd[4])));
+		float sa = sinf(alpha), ca = cosf(alpha);
+		if (ca <= 1.17549435e-38f || norm == 0.0f) { r.o = v3(1000.0f, 0.0f, 0.0f); r.d = v3(0.0f, 0.0f, 1.0f); return r; }
+		sa *= 1.0f / norm;
+		dl = v3(sa * xpix, sa * ypix, ca);
+	} else {
+		dl = v3((uvx - f.screen_center[0]) * fw / f.focal_length[0], (uvy - f.screen_center[1]) * fh / f.focal_length[1], 1.0f);
+		if (f.camera_distortion_mode == 1) iterative_camera_undistortion(cd, dl.x, dl.y);
+	}
+	if (f.distortion_dev) {
+		float ox, oy;
+		read_image2(f.distortion_dev, f.distortion_resolution[0], f.distortion_resolution[1], uvx, uvy, ox, oy);
+		dl.x += ox; dl.y += oy;
+	}
+	V3 d = matvec3(cam, dl);
+	V3 o = v3(cam[9], cam[10], cam[11]);
+	if (f.dof != 0.0f) {
+		const V3 lookat = v3(o.x + d.x * f.focus_z, o.y + d.y * f.focus_z, o.z + d.z * f.focus_z);
+		float sx, sy;
+		ld_random_val_2d_general(f.spp_index, px * 19349663u + py * 96925573u, sx, sy);
+		const float a = sx * 2.0f - 1.0f, b = sy * 2.0f - 1.0f;  // square2disk_shirley
+		float rr, phi;
+		if (a * a > b * b) { rr = a; phi = (3.14159265358979323846f / 4.0f) * (b / a); }
+		else { rr = b; phi = (3.14159265358979323846f / 2.0f) - (3.14159265358979323846f / 4.0f) * (a / b); }
+		const float sp = sinf(phi), cp = cosf(phi);
+		const float bx = f.dof * (rr * cp), by = f.dof * (rr * sp);
+		o = v3(o.x + (cam[0] * bx + cam[3] * by), o.y + (cam[1] * bx + cam[4] * by), o.z + (cam[2] * bx + cam[5] * by));
+		d = v3((lookat.x - o.x) / f.focus_z, (lookat.y - o.y) / f.focus_z, (lookat.z - o.z) / f.focus_z);
+	}
+	const float n2 = d.x * d.x + d.y * d.y + d.z * d.z;
+	if (n2 > 0.0f) { const float n = sqrtf(n2); d = v3(d.x / n, d.y / n, d.z / n); }
+	r.o = o;
+	r.d = d;
+	Box aabb = mkbox(f.render_aabb_min, f.render_aabb_max);
+	float t = fmaxf(box_ray_tmin(aabb, r.o, r.d), NEAR_DISTANCE) + 1e-6f;
+	if (!box_contains(aabb, madd3(r.d, t, r.o))) return r;
+	r.t = t;
+	r.alive = true;
+	return r;
+}
+
+// glow_mode of composite_kernel_nerf (:807-903); returns the weight mask (mask_to_alpha)
+static float glow_apply(int glow_mode, float glow_y_cutoff, V3 pos, V3 cam_origin, float* rgb) {
+	float weight_mask = 1.0f, glow = 0.0f;
+	const bool green_grid = glow_mode & 1, green_cutline = glow_mode & 2, mask_to_alpha = glow_mode & 4, radial_mode = glow_mode & 8, grid_mode = glow_mode & 16;
+	float dist;
+	if (radial_mode) {
+		const V3 q = pos - cam_origin;
+		dist = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+		dist = fminf(dist, (4.5f - pos.y) * 0.333f);
+	} else {
+		dist = pos.y;
+	}
+	if (grid_mode) {
+		glow = 1.0f / fmaxf(1.0f, dist);
+	} else {
+		float y = glow_y_cutoff - dist;
+		float mask = 0.0f;
+		if (y > 0.0f) {
+			y *= 80.0f;
+			mask = fminf(1.0f, y);
+			if (green_cutline) glow += fmaxf(0.0f, 1.0f - fabsf(1.0f - y)) * 4.0f;
+			if (y > 1.0f) y = 1.0f - (y - 1.0f) * 0.05f;
+			if (green_grid) glow += fmaxf(0.0f, y / fmaxf(1.0f, dist));
+		}
+		if (mask_to_alpha) weight_mask = mask;
+	}
+	if (glow > 0.0f) {
+		float line = 0.0f;
+		const float pi = 3.141592653589793f;
+		for (int k = 0; k < 4; ++k) {
+			const float m = (float)(2 << k);
+			line += fmaxf(0.0f, cosf(pos.y * m * pi * 16.0f) - 0.975f);
+			line += fmaxf(0.0f, cosf(pos.x * m * pi * 16.0f) - 0.975f);
+			line += fmaxf(0.0f, cosf(pos.z * m * pi * 16.0f) - 0.975f);
+		}
+		if (grid_mode) {
+			glow = glow * line * 15.0f;
+			rgb[1] = glow; rgb[2] = glow * 0.5f; rgb[0] = glow * 0.25f;
+		} else {
+			glow = glow * glow * 0.25f + glow * line * 15.0f;
+			rgb[1] += glow; rgb[2] += glow * 0.5f; rgb[0] += glow * 0.25f;
+		}
+	}
+	return weight_mask;
+}
+
 Ray make_ray(const NsbFrame& f, uint32_t px, uint32_t py) {
+	if (general_camera(f)) return make_ray_general(f, px, py);
 	Ray r;
 	r.alive = false;
 	uint32_t W = (uint32_t)f.width, H = (uint32_t)f.height;
@@ -862,7 +1038,19 @@ int orc_render(const OrcScene* s, const NsbFrame* f, float* fb, float* depth, Or
 			depth[pix] = 1e10f; // :2581
 			if (margin) margin[pix] = 1e30f;
 			Ray r = make_ray(*f, (uint32_t)px, (uint32_t)py);
+			if (f->envmap_dev) read_envmap(f->envmap_dev, f->envmap_resolution[0], f->envmap_resolution[1], r.d, fb + 4 * (size_t)pix);  // :2581-2583, every pixel
 			if (!r.alive) continue;
+			if (f->render_mode == NSB_RENDER_DISTORTION) {  // :2596-2607
+				float dx = 0.5f, dy = 0.5f;
+				if (f->distortion_dev) {
+					read_image2(f->distortion_dev, f->distortion_resolution[0], f->distortion_resolution[1], ((float)px + 0.5f) / (float)W, ((float)py + 0.5f) / (float)H, dx, dy);
+					dx = dx * 50.0f + 0.5f; dy = dy * 50.0f + 0.5f;
+				}
+				float* o4 = fb + 4 * (size_t)pix;
+				o4[0] = dx; o4[1] = dy; o4[2] = 0.5f; o4[3] = 1.0f;
+				depth[pix] = 1.0f;
+				continue;
+			}
 			++n_alive;
 			V3 idir = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
 			float t = r.t;
@@ -927,6 +1115,10 @@ int orc_render(const OrcScene* s, const NsbFrame* f, float* fb, float* depth, Or
 				float weight = alpha * T;
 				float rgb[3];
 				for (int c = 0; c < 3; ++c) rgb[c] = network_to_rgb(h2f(out[c]), f->rgb_activation);
+				if (f->glow_mode) {  // :807-903
+					const float mask = glow_apply(f->glow_mode, f->glow_y_cutoff, cpos, cam_org, rgb);
+					if (f->glow_mode & 4) weight *= mask;
+				}
 				if (f->render_mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
 				else if (f->render_mode == NSB_RENDER_POSITIONS && f->show_accel) {  // :913-923: one random colour per occupancy cell
 					uint32_t mip = (uint32_t)std::max(f->min_mip, mip_from_pos(cpos));

@@ -77,7 +77,8 @@ struct CudaRenderBuffer {
 	bool dlss() const { return false; }
 };
 
-template <typename T> struct NullParams { T* params_inference() const { return nullptr; } };
+// m_envmap.envmap / m_distortion.map are tcnn trainable buffers in the reference; here a view of the caller's texels (null = none)
+template <typename T> struct NullParams { T* p = nullptr; T* params_inference() const { return p; } };
 
 // testbed.h: the Testbed members read by render_nerf (testbed_nerf.cu:3066-3201) and the NerfTracer class (:129-240), same names
 struct Testbed {
@@ -158,6 +159,28 @@ struct Testbed {
 	                 const Matrix<float, 3, 4>& camera_matrix0, const Matrix<float, 3, 4>& camera_matrix1, const Vector4f& rolling_shutter, const Vector2f& screen_center,
 	                 bool apply_operators, cudaStream_t stream);
 };
+
+// NsbFrame (ABI 3) -> the Testbed members render_nerf reads for the general camera, glow, environment and distortion maps
+static inline void set_frame_extras(Testbed& tb, const NsbFrame* f) {
+	tb.m_nerf.render_with_camera_distortion = f->camera_distortion_mode != 0 || f->distortion_dev != nullptr;
+	tb.m_nerf.render_distortion.mode = (ECameraDistortionMode)f->camera_distortion_mode;
+	for (int i = 0; i < 7; ++i) tb.m_nerf.render_distortion.params[i] = f->camera_distortion_params[i];
+	tb.m_dof = f->dof;
+	tb.m_slice_plane_z = 0.f;
+	tb.m_scale = f->focus_z > 0.f ? f->focus_z : 1.f;  // plane_z = m_slice_plane_z + m_scale
+	tb.m_nerf.m_glow_mode = f->glow_mode;
+	tb.m_nerf.m_glow_y_cutoff = f->glow_y_cutoff;
+	tb.m_envmap.envmap->p = const_cast<float*>(f->envmap_dev);
+	tb.m_envmap.resolution = Vector2i(f->envmap_resolution[0], f->envmap_resolution[1]);
+	tb.m_distortion.map->p = const_cast<float*>(f->distortion_dev);
+	tb.m_distortion.resolution = Vector2i(f->distortion_resolution[0], f->distortion_resolution[1]);
+}
+static inline CameraDistortion frame_camera_distortion(const NsbFrame* f) {
+	CameraDistortion cd;
+	cd.mode = (ECameraDistortionMode)f->camera_distortion_mode;
+	for (int i = 0; i < 7; ++i) cd.params[i] = f->camera_distortion_params[i];
+	return cd;
+}
 
 // ---- the reference's code ---------------------------------------------------------------------------------------------
 #include "testbed_nerf.inc"

@@ -145,8 +145,8 @@ int ref_march_trace(const NsbFrame* f, const uint8_t* bitfield, const uint32_t* 
 		const uint32_t pix = pixels[k], x = pix % W, y = pix / W;
 		blockDim = dim3(1, 1, 1); gridDim = dim3(W, H, 1); blockIdx = {x, y, 0}; threadIdx = {0, 0, 0};
 		init_rays_with_payload_kernel_nerf(f->spp_index, payloads.data(), Vector2i((int)W, (int)H), focal, c0, c1, rs, Vector2f(f->screen_center[0], f->screen_center[1]),
-		                                   (bool)f->snap_to_pixel_centers, render_aabb, 1.0f /*plane_z = m_slice_plane_z + m_scale*/, 0.0f, CameraDistortion{}, nullptr, Vector2i::Zero(),
-		                                   fb.data(), depth.data(), nullptr, Vector2i::Zero(), (ERenderMode)f->render_mode);
+		                                   (bool)f->snap_to_pixel_centers, render_aabb, f->focus_z > 0.f ? f->focus_z : 1.0f /*plane_z = m_slice_plane_z + m_scale*/, f->dof, frame_camera_distortion(f), nullptr, Vector2i::Zero(),
+		                                   fb.data(), depth.data(), f->distortion_dev, Vector2i(f->distortion_resolution[0], f->distortion_resolution[1]), (ERenderMode)f->render_mode);
 		NerfPayload& p = payloads[pix];
 		float* rr = ray + 8 * (size_t)k;
 		rr[0] = p.origin.x(); rr[1] = p.origin.y(); rr[2] = p.origin.z(); rr[3] = p.dir.x(); rr[4] = p.dir.y(); rr[5] = p.dir.z(); rr[6] = p.t;
@@ -188,6 +188,7 @@ int ref_render(const NsbFrame* f, const uint8_t* bitfield, const NsbEditOp* ops,
 		tb.m_nerf.density_activation = (ENerfActivation)f->density_activation;
 		tb.m_nerf.rendering_min_transmittance = f->min_transmittance;
 		tb.m_nerf.tracer.m_poisson_target = f->poisson_target != 0;
+		set_frame_extras(tb, f);
 		for (int i = 0; i < n_ops; ++i) tb.m_nerf.tracer.add_edit_operator(make_op(ops[i]));
 		NerfNetwork<network_precision_t> net; net.fn = fn; net.user = user;
 		CudaRenderBuffer rb; rb.res = Vector2i(f->width, f->height); rb.m_spp = f->spp_index; rb.fb = (Array4f*)fb; rb.depth = depth;

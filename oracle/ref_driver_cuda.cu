@@ -91,6 +91,7 @@ static void configure(RefCuScene& sc, const NsbFrame* f) {
 	tb.m_nerf.density_activation = (ENerfActivation)f->density_activation;
 	tb.m_nerf.rendering_min_transmittance = f->min_transmittance;
 	tb.m_nerf.tracer.m_poisson_target = f->poisson_target != 0;
+	set_frame_extras(tb, f);  // ABI 3: general camera, glow, environment / distortion maps (device pointers)
 }
 
 extern "C" {
@@ -159,8 +160,8 @@ int refcu_march_trace(void* scene, const NsbFrame* f, const uint32_t* pixels, ui
 		fb.memset(0);
 		tb.m_nerf.tracer.init_rays_from_camera(f->spp_index, 16, 0, Vector2i((int)W, (int)H), Vector2f(f->focal_length[0], f->focal_length[1]), cam34(f->camera0), cam34(f->camera1),
 		                                        Vector4f(f->rolling_shutter[0], f->rolling_shutter[1], f->rolling_shutter[2], f->rolling_shutter[3]),
-		                                        Vector2f(f->screen_center[0], f->screen_center[1]), tb.m_snap_to_pixel_centers, tb.m_render_aabb, 1.0f, 0.0f, CameraDistortion{}, nullptr,
-		                                        Vector2i::Zero(), nullptr, Vector2i::Zero(), fb.data(), depth.data(), tb.m_nerf.density_grid_bitfield.data(), tb.m_nerf.show_accel,
+		                                        Vector2f(f->screen_center[0], f->screen_center[1]), tb.m_snap_to_pixel_centers, tb.m_render_aabb, tb.m_slice_plane_z + tb.m_scale, tb.m_dof, frame_camera_distortion(f), nullptr,
+		                                        Vector2i::Zero(), f->distortion_dev, Vector2i(f->distortion_resolution[0], f->distortion_resolution[1]), fb.data(), depth.data(), tb.m_nerf.density_grid_bitfield.data(), tb.m_nerf.show_accel,
 		                                        tb.m_nerf.cone_angle_constant, (ERenderMode)f->render_mode, nullptr);
 		NerfPayload* payloads_dev = tb.m_nerf.tracer.rays_init().payload;
 		std::vector<NerfPayload> payloads(N);
