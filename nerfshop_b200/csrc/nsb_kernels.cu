@@ -194,6 +194,20 @@ constexpr uint32_t RENDER_TMEM_COLS = NSB_TILES <= 1 ? 64 : NSB_TILES <= 2 ? 128
 // OPS = false: the instantiation for frames without edit operators (f.apply_ops == 0 or no operator uploaded) carries none of the deform /
 // membrane code in its hot loop (the loop has to fit the instruction cache: profiles/README.md item 6).
 // ACC16: the MLP accumulator policy (nsb_set_mlp_accumulator): fp16 TMEM accumulators, like the reference's wmma __half fragments.
+// experiment switches (tools/ab_kernels.py variants): compile a feature of the fused kernel out to measure what its presence costs the default path
+#ifndef NSB_X_ACCEL
+#define NSB_X_ACCEL 1
+#endif
+#ifndef NSB_X_GLOW
+#define NSB_X_GLOW 1
+#endif
+#ifndef NSB_X_RAYOD
+#define NSB_X_RAYOD 1
+#endif
+#ifndef NSB_X_HELP
+#define NSB_X_HELP 0  // helper lanes: measured slower when used AND 5 % slower by their mere presence in the loop (register allocation / code layout):
+                      // compiled out of the product; `build.build_variant("helpers", ["NSB_X_HELP=1"])` is the experiment build NSB_HELPERS acts on
+#endif
 template <bool OPS, bool ACC16>
 __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
@@ -240,8 +254,11 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 	// occupied in-bounds sample, where the ordinary march resumes next round. Samples past a ray's termination are evaluated and discarded, like the
 	// reference's own n_steps > 1 batching; frames are bit-identical with or without helpers. help_mode 1: only once the queue is exhausted, 2: always.
 	// MEASURED (profiles/README.md, round 2): 13.5 % fewer rounds but each round 27 % dearer — the loop's cost follows the samples evaluated (gather
-	// wavefronts + issue), not the rounds — so the default is 0 and this stays an opt-in experiment.
-	const int help_mode = (OPS || (f.glow_mode & 4)) ? 0 : (dda_flags >> 16) & 3;  // host: NSB_HELPERS (the mailbox does not carry glow's weight mask)
+	// wavefronts + issue), not the rounds — and the code's presence alone costs 5 %: it is compiled only into the experiment build (NSB_X_HELP=1).
+	const bool fx_show_accel = NSB_X_ACCEL && f.show_accel;
+	const int fx_glow = NSB_X_GLOW ? f.glow_mode : 0;
+	const float* const fx_ray_od = NSB_X_RAYOD ? ray_od : nullptr;
+	const int help_mode = (!NSB_X_HELP || OPS || (fx_glow & 4)) ? 0 : (dda_flags >> 16) & 3;  // host: NSB_HELPERS (the mailbox does not carry glow's weight mask)
 	constexpr uint32_t HELP_DEPTH = 7;
 	// mailbox helper -> owner: the tile's A-operand buffer is idle between the last MMA of a round and the next encode, and every warp only ever
 	// writes its own 32 rows of it: field q of lane l lives in k-chunk q, at this warp's 512 bytes
@@ -332,8 +349,8 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 					if (qi != 0xffffffffu) {
 						const RayRec rr = list[qi];
 						pix = rr.pix;
-						if (ray_od) {  // a general-camera frame: k_prepare_rays<true> left the ray next to its queue entry
-							const float* od = ray_od + 6 * (size_t)qi;
+						if (fx_ray_od) {  // a general-camera frame: k_prepare_rays<true> left the ray next to its queue entry
+							const float* od = fx_ray_od + 6 * (size_t)qi;
 							ro = v3(od[0], od[1], od[2]); rd = v3(od[3], od[4], od[5]);
 						} else {
 							Ray r;
@@ -485,16 +502,16 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 			} else {
 				alpha = 1.0f - __expf(-sigma * dtu);
 			}
-			if (f.show_accel) alpha = 1.0f;  // show_accel >= 0: the occupancy cells themselves are drawn (:788-790)
+			if (fx_show_accel) alpha = 1.0f;  // show_accel >= 0: the occupancy cells themselves are drawn (:788-790)
 			float rgb[3] = {network_to_rgb(h_lo(rgbo[0]), f.rgb_act), network_to_rgb(h_hi(rgbo[0]), f.rgb_act), network_to_rgb(h_lo(rgbo[1]), f.rgb_act)};
-			if (f.glow_mode) {  // :807-903, before the mode overrides
-				const float4 gl = glow_apply(f.glow_mode, f.glow_y_cutoff, cpos, v3(f.cam1[9], f.cam1[10], f.cam1[11]), rgb[0], rgb[1], rgb[2]);
+			if (fx_glow) {  // :807-903, before the mode overrides
+				const float4 gl = glow_apply(fx_glow, f.glow_y_cutoff, cpos, v3(f.cam1[9], f.cam1[10], f.cam1[11]), rgb[0], rgb[1], rgb[2]);
 				rgb[0] = gl.x; rgb[1] = gl.y; rgb[2] = gl.z; s_mask = gl.w;
 			}
 			if (f.mode != NSB_RENDER_SHADE) {
 				const V3 ro = v3(TB.ray[R_OX][rtid], TB.ray[R_OY][rtid], TB.ray[R_OZ][rtid]);
 				if (f.mode == NSB_RENDER_AO) { rgb[0] = rgb[1] = rgb[2] = alpha; }
-				else if (f.mode == NSB_RENDER_POSITIONS && f.show_accel) {  // one random colour per occupancy cell (:913-923)
+				else if (f.mode == NSB_RENDER_POSITIONS && fx_show_accel) {  // one random colour per occupancy cell (:913-923)
 					const uint32_t mip = (uint32_t)max(f.min_mip, mip_from_pos(cpos));
 					const float res = (float)(GRIDSIZE >> mip);
 					const int ix = (int)mul(cpos.x, res), iy = (int)mul(cpos.y, res), iz = (int)mul(cpos.z, res);
@@ -555,7 +572,7 @@ __global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFr
 					finish(false, cr, cg, cb, ca, ray_depth);
 				}
 			};
-			if (f.glow_mode & 4) {
+			if (fx_glow & 4) {
 				// mask_to_alpha: weight *= mask (a separate copy so that the unmasked expression — and its FMA contraction — stays exactly the reference's)
 				float T = 1.0f - ca;
 				float weight = s_alpha * T;
@@ -1098,7 +1115,7 @@ struct NsbContext {
 	size_t ray_od_capacity = 0;
 	int acc16 = 1;                 // MLP accumulator policy: 1 fp16 TMEM accumulators (default: the reference's wmma __half fragments), 0 fp32 (nsb_set_mlp_accumulator)
 	int use_ws = 0;                // NSB_WS=1: frames without operators go through the warp-specialised kernel (experimental; default k_render_fused<false>)
-	int helpers = 0;               // helper lanes of k_render_fused (frames without operators; experiment, measured slower: profiles/README.md): 0 off (default), 1 once the queue is exhausted, 2 always (NSB_HELPERS)
+	int helpers = 0;               // helper lanes of k_render_fused (experiment build only, -DNSB_X_HELP=1; measured slower: profiles/README.md): 0 off (default), 1 once the queue is exhausted, 2 always (NSB_HELPERS)
 	int refill_thr = 2;            // lanes of a warp refill when at most this many of its rays are alive (31: immediately)
 	int dda_budget = DDA_BUDGET;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;  // start, end, between k_prepare_rays and k_render_fused

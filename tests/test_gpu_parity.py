@@ -229,12 +229,17 @@ def test_full_size_properties(scene, renderer):
 
 def test_helper_lanes_do_not_change_the_frame(scene, monkeypatch):
     """k_render_fused lends the lanes without a ray to the rays that have one (up to 7 further samples per ray and round, composited in march
-    order by the ray's own lane; NSB_HELPERS, an opt-in experiment). Scheduling only: frames, depth and the ray / sample / hit counts are bit-identical
+    order by the ray's own lane; NSB_HELPERS in the experiment build -DNSB_X_HELP=1). Scheduling only: frames, depth and the ray / sample / hit counts are bit-identical
     with helpers off (0, the default), in the frame's tail only (1) and always (2) — at 1080p, at a ragged size, on a tile partition and in every render mode."""
     import torch
 
+    from nerfshop_b200 import build
     from nerfshop_b200.renderer import NerfRenderer
 
+    # the helper-lane code is compiled out of the product (its presence alone costs 5 %): this is the experiment build of the same sources
+    helpers_lib = os.path.join(build.LIB_DIR, "libnerfshop_b200_helpers.so")
+    if not os.path.exists(helpers_lib):
+        build.build_variant("helpers", ["NSB_X_HELP=1"])
     model, occ = scene
     cams = syn.orbit_cameras(120)
     jobs = [(syn.make_frame(model, cams[17], 1920, 1080), "1080p"), (syn.make_frame(model, cams[44], 333, 187), "ragged"),
@@ -246,7 +251,7 @@ def test_helper_lanes_do_not_change_the_frame(scene, monkeypatch):
     results = {}
     for helpers in ("0", "1", "2"):
         monkeypatch.setenv("NSB_HELPERS", helpers)
-        r = NerfRenderer(0)
+        r = NerfRenderer(0, lib_path=helpers_lib)
         r.upload_model(model.desc, model.params)
         r.upload_occupancy(occ)
         out = []
