@@ -9,8 +9,9 @@ parameters (no checkpoint ships with the reference). N > 1: image-plane tiles ar
 one NCCL all-gather assembles the framebuffer inside the step.
 
 value      : whole-job Mrays/s with the output staying in HBM (per-step CUDA-event time, max over ranks)
-e2e.value  : the same through the host-buffer entry point nsb_render_host: frame description host->device,
-             RGBA+depth framebuffer device->pinned host inside the timed region
+e2e.value  : the same with every frame delivered to pinned HOST memory inside the timed region, through the C ABI's host-buffer entry point
+             nsb_render_host_async / nsb_host_frame_wait (frame description host->device, RGBA+depth device->host; two frames in flight, so
+             the 41.5 MB copy of frame k overlaps the render of frame k+1; N > 1: rank 0 copies the gathered frame on a second stream)
 roofline   : the one kernel of the step (k_render_fused): algorithmic 512 B hash-grid gather per sample
               x samples of the frame / its CUDA-event duration, against measured HBM peak
 gpu_baseline: (N = 1) the reference's OWN CUDA path — Testbed::render_nerf, NerfTracer::trace and every kernel they launch, compiled
@@ -172,7 +173,7 @@ def cpu_reference_run(steps: int, warmup: int, threads: int | None = None):
 def measure_reference_cuda_and_edit_configs(r, model, occ, cams, fb, depth, flush, steps, dev):
     """N = 1 only. (1) gpu_baseline: the reference's CUDA path (oracle/_ref, nvcc build of /root/reference's render path; network = nsb_inference)
     on the orbit cameras of configs[1]. (2) configs[2] / configs[3] at 1080p, native and reference-CUDA. CUDA events around each frame, L2 flushed
-    between frames, 3 warm-up frames."""
+    between frames, 3 warm-up frames, median over the timed frames (both arms)."""
     import torch
 
     from nerfshop_b200 import editing, synthetic as syn
@@ -197,7 +198,7 @@ def measure_reference_cuda_and_edit_configs(r, model, occ, cams, fb, depth, flus
             torch.cuda.synchronize(dev)
             if i >= 3:
                 ms.append(e0.elapsed_time(e1))
-        return float(np.mean(ms)), ms
+        return float(np.median(ms)), ms  # median: the reference arm syncs with the host every round, one descheduled host thread would own a mean
 
     def both_arms(rr, rc, frames, n):
         nat_ms, _ = time_frames(lambda f: rr.render(f, fb, depth), frames, n)
@@ -340,7 +341,7 @@ def main():
     stream = torch.cuda.current_stream(dev)
     launches_per_step = 2 + (2 if world > 1 else 0)  # k_prepare_rays + k_render_fused (+ k_pack_tiles + k_unpack_gathered; the all-gather is NCCL's)
 
-    def device_step(i):
+    def device_step(i, fb=fb, depth=depth):
         """One frame, output left in HBM (for N > 1: render own tiles, pack, all-gather, unpack every shard)."""
         f = syn.make_frame(model, cams[(i * 7) % N_ORBIT], W, H, rank=rank, world=world)
         fb.zero_()  # render_buffer.clear_frame
@@ -385,27 +386,52 @@ def main():
     total_ms, wall, kern_ms, samples = timed(device_step, args.warmup, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: host buffers through nsb_render_host (single GPU) / gather then D2H on rank 0 (N > 1) ----
+    # ---- e2e: every step's frame ends in (pinned) HOST memory; the copy of frame k overlaps the render of frame k+1, two frames in flight ----
+    # N = 1: the C ABI's host-buffer entry point nsb_render_host_async / nsb_host_frame_wait (the consumer takes frame k-1 while frame k renders).
+    # N > 1: render + gather into one of two device framebuffers, rank 0 copies it out on a second stream.
+    host_fbs = [host_fb, torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()]
+    host_depths = [host_depth, torch.zeros((H, W), dtype=torch.float32).pin_memory()]
+    pending = {}
+    if world > 1:
+        fbs, depths = [fb, torch.zeros_like(fb)], [depth, torch.zeros_like(depth)]
+        copy_stream = torch.cuda.Stream(dev)
+        copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_step(i):
+        b = i & 1
         f = syn.make_frame(model, cams[(i * 7) % N_ORBIT], W, H, rank=rank, world=world)
         if world == 1:
-            r.render_to_cpu(f, host_fb, host_depth)
+            pending[b] = r.render_to_cpu_async(f, host_fbs[b], host_depths[b])
+            if (b ^ 1) in pending:
+                r.wait_host_frame(pending.pop(b ^ 1))  # frame i-1 is now in host_fbs[b ^ 1]
         else:
-            device_step(i)
+            stream.wait_event(copy_done[b])  # the copy that last read this framebuffer (two steps ago)
+            device_step(i, fbs[b], depths[b])
             if rank == 0:
-                host_fb.copy_(fb, non_blocking=True)
-                host_depth.copy_(depth, non_blocking=True)
-            torch.cuda.synchronize(dev)
+                done = torch.cuda.Event()
+                done.record(stream)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    host_fbs[b].copy_(fbs[b], non_blocking=True)
+                    host_depths[b].copy_(depths[b], non_blocking=True)
+                    copy_done[b].record(copy_stream)
+
+    def e2e_drain():
+        for t in list(pending.values()):
+            r.wait_host_frame(t)
+        pending.clear()
 
     def timed_wall(step_fn, n_warm, n_steps):
         for i in range(n_warm):
             step_fn(i)
+        e2e_drain()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(n_steps):
             step_fn(n_warm + i)
+        e2e_drain()  # the last frames' copies are inside the timed region
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -244,6 +244,12 @@ NsbStatus nsb_render(NsbContext* ctx, const NsbFrame* frame, float* fb_dev, floa
 /* Same through HOST buffers (the reference's Testbed::render_to_cpu recipe, python_api.cu:129-175):
  * clears a device framebuffer, renders, copies RGBA (+depth if non-NULL) back, synchronises. */
 NsbStatus nsb_render_host(NsbContext* ctx, const NsbFrame* frame, float* fb_host, float* depth_host);
+/* The same without the wait (new; the reference's render_to_cpu is synchronous): the frame is rendered into one of two device framebuffers the
+ * context owns and copied back on a second stream, so the copy of frame k (41.5 MB at 1080p) overlaps the render of frame k+1. Returns a ticket;
+ * fb_host / depth_host (pinned memory, or the copy is not asynchronous) belong to the library until nsb_host_frame_wait(ticket) returns. At most
+ * two frames are in flight: a third call waits for the oldest copy. */
+NsbStatus nsb_render_host_async(NsbContext* ctx, const NsbFrame* frame, float* fb_host, float* depth_host, uint64_t* ticket);
+NsbStatus nsb_host_frame_wait(NsbContext* ctx, uint64_t ticket);
 /* Synchronises and returns the counters of the last render. */
 NsbStatus nsb_get_stats(NsbContext* ctx, NsbRenderStats* out);
 

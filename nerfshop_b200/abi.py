@@ -131,7 +131,7 @@ EXPORTED_SYMBOLS = [
     "nsb_model_n_params", "nsb_set_mlp_accumulator", "nsb_upload_model", "nsb_upload_model_dev", "nsb_upload_occupancy_dev", "nsb_upload_occupancy", "nsb_upload_density_grid", "nsb_set_edit_ops",
     "nsb_update_density_grid", "nsb_download_density_grid", "nsb_cage_attach_mvc", "nsb_cage_deform", "nsb_cage_download",
     "nsb_poisson_boundary", "nsb_cage_set_membrane",
-    "nsb_render", "nsb_render_host", "nsb_get_stats", "nsb_debug_counters",
+    "nsb_render", "nsb_render_host", "nsb_render_host_async", "nsb_host_frame_wait", "nsb_get_stats", "nsb_debug_counters",
     "nsb_tiles_for_rank", "nsb_pack_tiles", "nsb_unpack_tiles", "nsb_unpack_gathered", "nsb_accumulate", "nsb_tonemap",
     "nsb_inference", "nsb_density", "nsb_encode", "nsb_map_rays", "nsb_poisson_residuals", "nsb_map_rays_op", "nsb_poisson_residuals_op",
     "nsb_map_positions", "nsb_poisson_residual_density", "nsb_march_trace",
@@ -185,6 +185,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.nsb_set_edit_ops.argtypes = [vp, C.POINTER(NsbEditOp), i32]
     lib.nsb_render.argtypes = [vp, C.POINTER(NsbFrame), vp, vp, vp]
     lib.nsb_render_host.argtypes = [vp, C.POINTER(NsbFrame), vp, vp]
+    lib.nsb_render_host_async.argtypes = [vp, C.POINTER(NsbFrame), vp, vp, C.POINTER(u64)]
+    lib.nsb_host_frame_wait.argtypes = [vp, u64]
     lib.nsb_get_stats.argtypes = [vp, C.POINTER(NsbRenderStats)]
     lib.nsb_debug_counters.argtypes = [vp, C.POINTER(u64), i32]
     lib.nsb_tiles_for_rank.argtypes = [i32, i32, i32, i32, C.POINTER(u32)]

@@ -1125,6 +1125,13 @@ struct NsbContext {
 	float* d_depth = nullptr;
 	size_t fb_pixels = 0;
 	cudaStream_t stream = nullptr;
+	// nsb_render_host_async: two framebuffers in flight, the D2H copy of one overlaps the render of the other
+	float* d_fb2[2] = {nullptr, nullptr};
+	float* d_depth2[2] = {nullptr, nullptr};
+	size_t fb2_pixels = 0;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t render_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+	uint64_t host_seq = 0;  // tickets issued
 };
 
 static uint32_t next_multiple_u32(uint32_t v, uint32_t m) { return ((v + m - 1) / m) * m; }
@@ -1189,6 +1196,11 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	CU(cudaEventCreate(&c->ev1));
 	CU(cudaEventCreate(&c->evm));
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i) {
+		CU(cudaEventCreateWithFlags(&c->render_done[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming));
+	}
 	// Shared memory and L1 share one 256 KB array per SM: every kernel asks for exactly the carve-out its resident CTAs need and
 	// leaves the rest to L1, which serves the hash-grid gathers (the default heuristic picks a carve-out too small for even one
 	// CTA; "max shared" starves L1 — the tile loop runs 44 % faster with 92 KB of L1 than with 28 KB, profiles/README.md).
@@ -1274,6 +1286,12 @@ extern "C" NsbStatus nsb_destroy(NsbContext* c) {
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->evm) cudaEventDestroy(c->evm);
 	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	for (int i = 0; i < 2; ++i) {
+		if (c->render_done[i]) cudaEventDestroy(c->render_done[i]);
+		if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
+		cudaFree(c->d_fb2[i]); cudaFree(c->d_depth2[i]);
+	}
 	delete c;
 	return NSB_OK;
 }
@@ -1926,6 +1944,48 @@ extern "C" NsbStatus nsb_render_host(NsbContext* c, const NsbFrame* frame, float
 	CU(cudaMemcpyAsync(fb_host, c->d_fb, n * 16, cudaMemcpyDeviceToHost, c->stream));
 	if (depth_host) CU(cudaMemcpyAsync(depth_host, c->d_depth, n * 4, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_render_host_async(NsbContext* c, const NsbFrame* frame, float* fb_host, float* depth_host, uint64_t* ticket) {
+	if (!c || !frame || !fb_host || !ticket) return fail(NSB_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(c->device));
+	const size_t n = (size_t)frame->width * (size_t)frame->height;
+	if (n == 0) return fail(NSB_ERR_INVALID, "empty frame");
+	if (n > c->fb2_pixels) {
+		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaStreamSynchronize(c->copy_stream));
+		for (int i = 0; i < 2; ++i) {
+			cudaFree(c->d_fb2[i]); cudaFree(c->d_depth2[i]);
+			c->d_fb2[i] = nullptr; c->d_depth2[i] = nullptr;
+		}
+		c->fb2_pixels = 0;
+		for (int i = 0; i < 2; ++i) {
+			CU(cudaMalloc(&c->d_fb2[i], n * 16));
+			CU(cudaMalloc(&c->d_depth2[i], n * 4));
+		}
+		c->fb2_pixels = n;
+	}
+	const int slot = (int)(c->host_seq & 1u);
+	if (c->host_seq >= 2) CU(cudaStreamWaitEvent(c->stream, c->copy_done[slot], 0));  // the copy that last read this slot (two tickets ago)
+	CU(cudaMemsetAsync(c->d_fb2[slot], 0, n * 16, c->stream));  // render_buffer.clear_frame (testbed.cu:2635)
+	CU(cudaMemsetAsync(c->d_depth2[slot], 0, n * 4, c->stream));
+	NsbStatus st = nsb_render(c, frame, c->d_fb2[slot], c->d_depth2[slot], c->stream);
+	if (st != NSB_OK) return st;
+	CU(cudaEventRecord(c->render_done[slot], c->stream));
+	CU(cudaStreamWaitEvent(c->copy_stream, c->render_done[slot], 0));
+	CU(cudaMemcpyAsync(fb_host, c->d_fb2[slot], n * 16, cudaMemcpyDeviceToHost, c->copy_stream));
+	if (depth_host) CU(cudaMemcpyAsync(depth_host, c->d_depth2[slot], n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+	CU(cudaEventRecord(c->copy_done[slot], c->copy_stream));
+	*ticket = c->host_seq++;
+	return NSB_OK;
+}
+
+extern "C" NsbStatus nsb_host_frame_wait(NsbContext* c, uint64_t ticket) {
+	if (!c) return fail(NSB_ERR_INVALID, "null context");
+	if (ticket >= c->host_seq) return fail(NSB_ERR_INVALID, "ticket %llu was never issued", (unsigned long long)ticket);
+	CU(cudaSetDevice(c->device));
+	CU(cudaEventSynchronize(c->copy_done[ticket & 1u]));  // if the slot was reused since, this is the later copy, which started after this one finished
 	return NSB_OK;
 }
 

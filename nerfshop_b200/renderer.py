@@ -183,6 +183,18 @@ class NerfRenderer:
         abi.check(self.lib, self.lib.nsb_render_host(self.ctx, C.byref(frame), fp, dp), "nsb_render_host")
         return fb_host, depth_host
 
+    def render_to_cpu_async(self, frame: abi.NsbFrame, fb_host, depth_host=None) -> int:
+        """nsb_render_host_async: returns a ticket; fb_host / depth_host (pinned) are valid after wait_host_frame(ticket). The copy of this frame
+        overlaps the render of the next one."""
+        fp = fb_host.data_ptr() if hasattr(fb_host, "data_ptr") else fb_host.ctypes.data
+        dp = None if depth_host is None else (depth_host.data_ptr() if hasattr(depth_host, "data_ptr") else depth_host.ctypes.data)
+        ticket = C.c_uint64()
+        abi.check(self.lib, self.lib.nsb_render_host_async(self.ctx, C.byref(frame), fp, dp, C.byref(ticket)), "nsb_render_host_async")
+        return ticket.value
+
+    def wait_host_frame(self, ticket: int) -> None:
+        abi.check(self.lib, self.lib.nsb_host_frame_wait(self.ctx, ticket), "nsb_host_frame_wait")
+
     def stats(self) -> abi.NsbRenderStats:
         st = abi.NsbRenderStats()
         abi.check(self.lib, self.lib.nsb_get_stats(self.ctx, C.byref(st)), "nsb_get_stats")

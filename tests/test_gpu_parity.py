@@ -268,6 +268,26 @@ def test_helper_lanes_do_not_change_the_frame(scene, monkeypatch):
             assert torch.equal(fb, fb0) and torch.equal(d, d0), (helpers, name)
 
 
+def test_async_host_frames_equal_the_synchronous_ones(scene, renderer):
+    """nsb_render_host_async / nsb_host_frame_wait: five frames through two slots in flight equal nsb_render_host's, tickets count up, and a bad
+    ticket is an error."""
+    import torch
+
+    model, _ = scene
+    cams = syn.orbit_cameras(120)
+    W, H = 320, 180
+    frames = [syn.make_frame(model, cams[(11 * k) % 120], W, H) for k in range(5)]
+    want = [tuple(a.copy() for a in renderer.render_to_cpu(f)) for f in frames]
+    host = [(torch.zeros((H, W, 4)).pin_memory(), torch.zeros((H, W)).pin_memory()) for _ in range(5)]
+    tickets = [renderer.render_to_cpu_async(f, *host[k]) for k, f in enumerate(frames)]
+    assert tickets == list(range(tickets[0], tickets[0] + 5))
+    for k in (4, 3, 0, 1, 2):
+        renderer.wait_host_frame(tickets[k])
+    for k in range(5):
+        assert np.array_equal(host[k][0].numpy(), want[k][0]) and np.array_equal(host[k][1].numpy(), want[k][1])
+    assert renderer.lib.nsb_host_frame_wait(renderer.ctx, tickets[-1] + 1) == abi.NSB_ERR_INVALID
+
+
 def test_no_model_is_an_error(built_lib):
     import ctypes as C
 
