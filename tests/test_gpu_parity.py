@@ -238,7 +238,7 @@ def test_helper_lanes_do_not_change_the_frame(scene, monkeypatch):
 
     # the helper-lane code is compiled out of the product (its presence alone costs 5 %): this is the experiment build of the same sources
     helpers_lib = os.path.join(build.LIB_DIR, "libnerfshop_b200_helpers.so")
-    if not os.path.exists(helpers_lib):
+    if not os.path.exists(helpers_lib) or os.path.getmtime(helpers_lib) < os.path.getmtime(build.build()):
         build.build_variant("helpers", ["NSB_X_HELP=1"])
     model, occ = scene
     cams = syn.orbit_cameras(120)
