@@ -457,7 +457,7 @@ def main():
         achieved = s_mean * BYTES_PER_SAMPLE / (k_ms * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 (fp32 accumulate/composite)",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 (hash features, MLP operands and tcgen05 accumulators, as the reference's wmma half fragments; fp32 march / deform / composite)",
             "data": "synthetic", "fps": 1e3 / ms_per_step,
             "config": dict(config, l2="flushed between timed steps (256 MiB memset outside the per-step event bracket)",
                            samples_per_frame=s_mean * world, samples_per_ray=s_mean * world / (W * H)),
