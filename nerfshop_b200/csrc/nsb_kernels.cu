@@ -170,8 +170,14 @@ enum { R_OX = 0, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_T, R_CR, R_CG, R_CB, R_CA, R_DE
 // weight image — four separate CTAs would hold four copies — which matters because shared memory is carved out of the same
 // 256 KB as the L1 that serves the hash-grid gathers: 4 x 43.6 KB CTAs leave ~60 KB of L1, one 4-tile CTA (112 KB) leaves ~124 KB
 // (profiles/README.md: the tile loop runs 44 % faster with 92 KB of L1 than with 28 KB).
+// How many: as many as the register file allows without spilling. Frames without operators need 80 registers per thread -> 6 tiles (24 warps per SM,
+// 158 KB of shared memory, ~97 KB of L1): 10.96 ms per 1080p frame against 12.63 ms with 4 tiles and 11.51 ms with 5 (round 2, profiles/README.md
+// item 23; round 1's fatter loop spilled beyond 4). Frames with operators carry the deform / membrane state: 5 tiles (96 registers, 40 B spilled).
 #ifndef NSB_TILES
-#define NSB_TILES 4
+#define NSB_TILES 6
+#endif
+#ifndef NSB_TILES_OPS
+#define NSB_TILES_OPS 5
 #endif
 struct TileBlock {
 	union {
@@ -182,14 +188,17 @@ struct TileBlock {
 	uint64_t mma_bar;
 	uint64_t pad[15];
 };
-struct __align__(128) RenderSmem {
+template <int TILES>
+struct __align__(128) RenderSmemT {
 	uint8_t w[tc::W_BYTES];
-	TileBlock tile[NSB_TILES];
+	TileBlock tile[TILES];
 	uint64_t w_bar;
 	uint32_t tmem_base;
 	uint32_t pad;
 };
-constexpr uint32_t RENDER_TMEM_COLS = NSB_TILES <= 1 ? 64 : NSB_TILES <= 2 ? 128 : NSB_TILES <= 4 ? 256 : 512;
+__host__ __device__ constexpr int render_tiles(bool ops) { return ops ? NSB_TILES_OPS : NSB_TILES; }
+__host__ __device__ constexpr uint32_t render_tmem_cols(int tiles) { return tiles <= 1 ? 64u : tiles <= 2 ? 128u : tiles <= 4 ? 256u : 512u; }
+static_assert(NSB_TILES >= 1 && NSB_TILES <= 8 && NSB_TILES_OPS >= 1 && NSB_TILES_OPS <= 8, "64 TMEM columns per tile, 512 per SM");
 
 // OPS = false: the instantiation for frames without edit operators (f.apply_ops == 0 or no operator uploaded) carries none of the deform /
 // membrane code in its hot loop (the loop has to fit the instruction cache: profiles/README.md item 6).
@@ -209,24 +218,27 @@ constexpr uint32_t RENDER_TMEM_COLS = NSB_TILES <= 1 ? 64 : NSB_TILES <= 2 ? 128
                       // compiled out of the product; `build.build_variant("helpers", ["NSB_X_HELP=1"])` is the experiment build NSB_HELPERS acts on
 #endif
 template <bool OPS, bool ACC16>
-__global__ void __launch_bounds__(128 * NSB_TILES, 1) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
+__global__ void __launch_bounds__(128 * render_tiles(OPS), 1) k_render_fused(const DevFrame f, const DevModel m, const uint8_t* __restrict__ bitfield,
                                                       const DevOp* __restrict__ ops, const int n_ops, const int any_poisson,
                                                       float4* __restrict__ fb, float* __restrict__ depth_out, const RayRec* __restrict__ list,
                                                       const float* __restrict__ ray_od, const uint32_t* __restrict__ n_queued_ptr, uint32_t* fetch_counter,
                                                       unsigned long long* __restrict__ stats, const int refill_thr, const int dda_flags) {
 	extern __shared__ __align__(128) uint8_t smem_raw[];
+	constexpr int TILES = render_tiles(OPS);
+	constexpr uint32_t RENDER_TMEM_COLS = render_tmem_cols(TILES);
+	using RenderSmem = RenderSmemT<TILES>;
 	RenderSmem& RS = *reinterpret_cast<RenderSmem*>(smem_raw);
 	const uint32_t tid = threadIdx.x & 127u;      // slot / row within the tile
 	const uint32_t tile = threadIdx.x >> 7;
 	TileBlock& TB = RS.tile[tile];
 	const uint32_t lane = tid & 31u;
 	const uint32_t n_queued = *n_queued_ptr;
-	if (blockIdx.x * 128u * NSB_TILES >= n_queued && blockIdx.x > 0) return;  // nothing this CTA could ever fetch
+	if (blockIdx.x * 128u * TILES >= n_queued && blockIdx.x > 0) return;  // nothing this CTA could ever fetch
 
 	// CTA setup: barriers, TMEM (64 columns per tile), one bulk-TMA copy of the weight image
 	if (threadIdx.x == 0) {
 		tc::mbar_init(&RS.w_bar, 1);
-		for (int t = 0; t < NSB_TILES; ++t) tc::mbar_init(&RS.tile[t].mma_bar, 1);
+		for (int t = 0; t < TILES; ++t) tc::mbar_init(&RS.tile[t].mma_bar, 1);
 		tc::fence_mbar_init();
 	}
 	if (threadIdx.x < 32) tc::tmem_alloc(&RS.tmem_base, RENDER_TMEM_COLS);
@@ -1212,13 +1224,13 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 		if (pct > 100) pct = 100;
 		return cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 	};
-	// k_render_fused: ONE CTA of NSB_TILES tiles per SM (512 threads x 128 registers = the whole register file; TMEM 64 columns
+	// k_render_fused: ONE CTA of NSB_TILES (NSB_TILES_OPS with operators) tiles per SM (768 x 80 / 640 x 96 registers = the register file; TMEM 64 columns
 	// per tile; shared memory 20 KB weights + 23 KB per tile).
 	c->ctas_per_sm = 1;
-	CU(set_smem((const void*)k_render_fused<false, false>, sizeof(RenderSmem), 1));
-	CU(set_smem((const void*)k_render_fused<true, false>, sizeof(RenderSmem), 1));
-	CU(set_smem((const void*)k_render_fused<false, true>, sizeof(RenderSmem), 1));
-	CU(set_smem((const void*)k_render_fused<true, true>, sizeof(RenderSmem), 1));
+	CU(set_smem((const void*)k_render_fused<false, false>, sizeof(RenderSmemT<render_tiles(false)>), 1));
+	CU(set_smem((const void*)k_render_fused<true, false>, sizeof(RenderSmemT<render_tiles(true)>), 1));
+	CU(set_smem((const void*)k_render_fused<false, true>, sizeof(RenderSmemT<render_tiles(false)>), 1));
+	CU(set_smem((const void*)k_render_fused<true, true>, sizeof(RenderSmemT<render_tiles(true)>), 1));
 	cudaFuncAttributes fa;
 	CU(cudaFuncGetAttributes(&fa, k_render_fused<false, false>));
 	const int by_smem_tile = (int)(prop.sharedMemPerMultiprocessor / (sizeof(tc::TileSmem) + 1024));
@@ -1253,8 +1265,8 @@ extern "C" NsbStatus nsb_create(int device, NsbContext** out) {
 	if (const char* e = getenv("NSB_CHUNK")) { int v = atoi(e); if (v >= 0 && v <= 65535) c->refill_thr |= v << 8; }
 	if (const char* e = getenv("NSB_DDA_BUDGET")) { int v = atoi(e); if (v >= 0 && v <= 1024) c->dda_budget = v; }
 	if (getenv("NSB_VERBOSE"))
-		fprintf(stderr, "[nsb] device %d: %d SMs; k_render_fused %d tiles/CTA, %d regs, %zu B smem; inference %d CTAs/SM, grid update %d CTAs/SM\n", device, c->sm_count,
-		        NSB_TILES, fa.numRegs, sizeof(RenderSmem), c->inference_ctas_per_sm, c->grid_update_ctas_per_sm);
+		fprintf(stderr, "[nsb] device %d: %d SMs; k_render_fused %d tiles/CTA (%d with operators), %d regs, %zu B smem; inference %d CTAs/SM, grid update %d CTAs/SM\n", device, c->sm_count,
+		        render_tiles(false), render_tiles(true), fa.numRegs, sizeof(RenderSmemT<render_tiles(false)>), c->inference_ctas_per_sm, c->grid_update_ctas_per_sm);
 	*out = c;
 	return NSB_OK;
 }
@@ -1903,9 +1915,10 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 			                                                                          nullptr, c->d_counters, (uint32_t)n_local, c->d_stats);
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(c->evm, stream));
-		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
-		if (grid > (my_tiles + NSB_TILES - 1) / NSB_TILES) grid = (uint32_t)((my_tiles + NSB_TILES - 1) / NSB_TILES);
 		const bool ops_on = f.apply_ops && c->n_ops > 0;
+		const uint32_t tiles = (uint32_t)render_tiles(ops_on);
+		uint32_t grid = (uint32_t)(c->sm_count * c->ctas_per_sm);
+		if (grid > (my_tiles + tiles - 1) / tiles) grid = (my_tiles + tiles - 1) / tiles;
 		if (!ops_on && c->use_ws && !c->acc16 && !f.show_accel && !f.general_camera && !f.glow_mode && (uint64_t)f.W * (uint64_t)f.H < (1ull << 28)) {  // k_render_ws ships the pixel in 28 bits of a flag word
 			uint32_t g2 = (uint32_t)c->sm_count;
 			if (g2 > (my_tiles + ws::PT - 1) / ws::PT) g2 = (uint32_t)((my_tiles + ws::PT - 1) / ws::PT);
@@ -1913,7 +1926,7 @@ extern "C" NsbStatus nsb_render(NsbContext* c, const NsbFrame* frame, float* fb_
 			                                                           c->d_counters, c->d_counters + 1, c->d_stats, c->refill_thr, c->dda_budget);
 		} else {
 		auto kernel = ops_on ? (c->acc16 ? k_render_fused<true, true> : k_render_fused<true, false>) : (c->acc16 ? k_render_fused<false, true> : k_render_fused<false, false>);
-		kernel<<<grid, 128 * NSB_TILES, sizeof(RenderSmem), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
+		kernel<<<grid, 128 * tiles, ops_on ? sizeof(RenderSmemT<render_tiles(true)>) : sizeof(RenderSmemT<render_tiles(false)>), stream>>>(f, c->model, c->has_occ ? c->d_bitfield : nullptr, c->d_ops, c->n_ops, c->any_poisson,
 		                                                          reinterpret_cast<float4*>(fb_dev), depth_dev, c->d_list, ray_od, c->d_counters, c->d_counters + 1, c->d_stats,
 		                                                          c->refill_thr, c->dda_budget | (c->helpers << 16));
 		}
