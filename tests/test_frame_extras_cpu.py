@@ -106,3 +106,39 @@ def test_ray_stream_with_lens_distortion(scene, oracle):
     d = np.abs(first_o - rec_r[both, 0, 7])
     print(f"\nlens-distorted, defocused ray stream: {both.sum()} rays; sample counts equal on {(cnt_o == cnt_r).mean() * 100:.2f} %; first-sample t: median diff {np.median(d):.2e}, max {d.max():.2e}")
     assert np.median(d) < 1e-6 and (d > 1e-4).mean() < 0.02
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_general_cameras_ray_stream(scene, oracle, seed):
+    """Random lens distortion (both models), distortion-map amplitude, aperture, focus distance, sample index and rolling shutter: the oracle's
+    rays and first samples against the reference kernels' (init_rays_with_payload_kernel_nerf + advance_pos_nerf), pixel for pixel."""
+    model, occ = scene
+    rng = np.random.default_rng(1000 + seed)
+    w, h = 80, 45
+    f = syn.make_frame(model, syn.orbit_cameras(120)[int(rng.integers(0, 120))], w, h, spp=int(rng.integers(0, 64)))
+    if rng.random() < 0.5:
+        syn.set_camera_distortion(f, abi.NSB_CAMERA_DISTORTION_ITERATIVE, list(rng.uniform(-1, 1, 4) * np.array([0.15, 0.05, 0.01, 0.01])))
+    else:
+        syn.set_camera_distortion(f, abi.NSB_CAMERA_DISTORTION_FTHETA, [0.0, rng.uniform(0.8, 1.2) / h, 0.0, rng.uniform(-3e-8, 3e-8), 0.0, w, h])
+    dist = syn.make_distortion_map(amplitude=float(rng.uniform(0.0, 0.02)), seed=seed)
+    if rng.random() < 0.7:
+        syn.set_maps(f, distortion_ptr=dist.ctypes.data, distortion_shape=dist.shape)
+    if rng.random() < 0.7:
+        f.dof, f.focus_z = float(rng.uniform(0.002, 0.03)), float(rng.uniform(0.6, 2.0))
+    f.rolling_shutter[1] = float(rng.uniform(0.0, 0.3))
+    f.rolling_shutter[3] = float(rng.uniform(0.0, 0.2))
+    cam1 = np.array(list(f.camera1), np.float32)
+    cam1[9:12] += rng.uniform(-0.02, 0.02, 3).astype(np.float32)  # camera0 != camera1: the rolling shutter interpolates them
+    for i in range(12):
+        f.camera0[i] = float(cam1[i])
+    pix = np.arange(w * h, dtype=np.uint32)
+    MS = 8
+    rec_o, idx_o, cnt_o = oracle.march_trace(f, pix, MS)
+    rec_r, ray_r, cnt_r, alive_r = ref.march_trace(f, occ, pix, MS)
+    cnt_o = np.minimum(cnt_o, MS)
+    both = (cnt_o > 0) & (cnt_r > 0)
+    d = np.abs((rec_o[both, 0, 0] + rec_o[both, 0, 1]).astype(np.float32) - rec_r[both, 0, 7])
+    print(f"\nseed {seed}: {both.sum()} rays with samples; counts equal on {(cnt_o == cnt_r).mean() * 100:.2f} %; first-sample t identical on {(d == 0).mean() * 100:.2f} %, max diff {d.max():.2e}")
+    assert both.sum() > 300
+    assert (cnt_o == cnt_r).mean() > 0.98
+    assert (d == 0).mean() > 0.95 and (d > 1e-4).mean() < 0.02
