@@ -291,3 +291,35 @@ def test_tet_grid_vs_reference_build_tet_grid(scene):
     assert np.array_equal(cage.original_bitfield, obits_ref), f"{np.count_nonzero(cage.original_bitfield != obits_ref)} canonical-bitfield bytes differ"
     bb = np.stack([cage.vertices.min(0), cage.vertices.max(0)])
     assert np.array_equal(bb, bbox_ref[:2]) or np.allclose(bb, bbox_ref[:2], atol=0), (bb, bbox_ref)
+
+
+def test_occupancy_update_sample_draw_vs_reference_kernel(scene, oracle):
+    """Row (f)-2: generate_grid_samples_nerf_nonuniform (common_nerf.cu:179-208), the reference's own kernel, against the sample draw inside the
+    oracle's update_density_grid — both launches (uniform, then non-uniform on m_rng advanced by 2^32), warped positions bit for bit."""
+    from nerfshop_b200.rng import Pcg32
+
+    rng0 = Pcg32(4242)
+    grid0 = np.zeros(abi.NSB_GRID_CELLS, np.float32)
+    grid0[::3] = 0.02      # cells above the non-uniform threshold 0.01
+    grid0[5::7] = -1.0     # untrained cells both passes must step over
+    n_uni, n_non, step, n_casc = 20_000, 12_000, 7, 3
+    u = abi.NsbGridUpdate()
+    u.n_uniform_samples, u.n_nonuniform_samples, u.reset_grid, u.n_cascades = n_uni, n_non, 0, n_casc
+    u.decay, u.ema_step, u.rng_state, u.rng_inc = 0.95, step, rng0.state, rng0.inc
+    u.train_aabb_min[:] = (-1.5, -1.5, -1.5)
+    u.train_aabb_max[:] = (2.5, 2.5, 2.5)
+    u.density_activation, u.apply_operators = abi.NSB_ACT_EXPONENTIAL, 0
+    _, _, _, samples = oracle.update_density_grid(u, grid0, want_samples=True)
+    amin, amax = np.array(list(u.train_aabb_min), np.float32), np.array(list(u.train_aabb_max), np.float32)
+    pos1, idx1 = ref.grid_samples(n_uni, rng0.state, rng0.inc, step, amin, amax, grid0, n_casc, -0.01)
+    r2 = rng0.copy()
+    r2.advance(1 << 32)  # m_rng.advance() between the two launches (testbed_nerf.cu:3576)
+    pos2, idx2 = ref.grid_samples(n_non, r2.state, r2.inc, step, amin, amax, grid0, n_casc, 0.01)
+    # both are warp_position(pos, aabb): what NerfNetwork::density is fed
+    got = samples[:, :3]
+    want = np.concatenate([pos1, pos2])
+    same = (got == want).all(axis=1)
+    print(f"\noccupancy-update sample draw: {same.sum()} of {same.size} warped positions identical; max |diff| {np.abs(got - want).max():.2e}")
+    assert same.mean() > 0.999 and np.abs(got - want).max() < 1e-6
+    G = 128 ** 3
+    assert (idx1 < n_casc * G).all() and (idx2 < n_casc * G).all() and (grid0[idx2] > 0.01).mean() > 0.9  # ten tries at one cell in three
