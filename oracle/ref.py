@@ -158,6 +158,15 @@ def grid_samples(n, rng_state, rng_inc, step, amin, amax, grid, n_cascades, thre
     return pos, idx
 
 
+def grid_to_bitfield(grid, mean: float):
+    """grid_to_bitfield + bitfield_max_pool (testbed_nerf.cu:514-555) as update_density_grid_mean_and_bitfield launches them."""
+    grid = f32(grid)
+    bits = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8)
+    lib().ref_grid_to_bitfield.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    lib().ref_grid_to_bitfield(_p(grid), float(mean), _p(bits))
+    return bits
+
+
 def march_trace(frame: abi.NsbFrame, bitfield, pixels, max_samples: int):
     pixels = u32(pixels)
     n = pixels.size

@@ -126,6 +126,16 @@ void ref_grid_samples(uint32_t n, uint64_t rng_state, uint64_t rng_inc, uint32_t
 	for (uint32_t i = 0; i < n; ++i) { out_pos[3 * i] = pos[i].p.x(); out_pos[3 * i + 1] = pos[i].p.y(); out_pos[3 * i + 2] = pos[i].p.z(); }
 }
 
+// Testbed::update_density_grid_mean_and_bitfield (testbed_nerf.cu:3642-3658) after its reduce_sum: grid_to_bitfield over all cascades with the given
+// mean, then bitfield_max_pool level by level. grid: float[5*128^3]; bits: uint8[5*128^3/8].
+void ref_grid_to_bitfield(const float* grid, float mean, uint8_t* bits) {
+	const uint32_t n_elements = NERF_GRIDSIZE() * NERF_GRIDSIZE() * NERF_GRIDSIZE();
+	memset(bits, 0, grid_mip_offset(NERF_CASCADES()) / 8);
+	tcnn::linear_kernel(grid_to_bitfield, 0, nullptr, n_elements / 8 * NERF_CASCADES(), grid, bits, &mean);
+	for (uint32_t level = 1; level < NERF_CASCADES(); ++level)
+		tcnn::linear_kernel(bitfield_max_pool, 0, nullptr, n_elements / 64, bits + grid_mip_offset(level - 1) / 8, bits + grid_mip_offset(level) / 8);
+}
+
 // ---- ray generation + occupancy march with the reference's kernels, one sample per call of generate_next (n_steps = 1) ----
 // For every listed pixel: init_rays_with_payload_kernel_nerf -> advance_pos_nerf -> generate_next_nerf_network_inputs x max_samples.
 // rec: per pixel per sample 8 floats = the NerfCoordinate the reference would feed the network (warped pos 3, warped dt, warped dir 3)

@@ -323,3 +323,27 @@ def test_occupancy_update_sample_draw_vs_reference_kernel(scene, oracle):
     assert same.mean() > 0.999 and np.abs(got - want).max() < 1e-6
     G = 128 ** 3
     assert (idx1 < n_casc * G).all() and (idx2 < n_casc * G).all() and (grid0[idx2] > 0.01).mean() > 0.9  # ten tries at one cell in three
+
+
+@pytest.mark.parametrize("fill", ["sparse", "dense_low"])
+def test_bitfield_from_density_grid_vs_reference_kernels(fill):
+    """Row (f)-2 / snapshot load: grid_to_bitfield + bitfield_max_pool (testbed_nerf.cu:514-555), launched as update_density_grid_mean_and_bitfield
+    does (:3642-3658), against the oracle's density-grid -> bitfield conversion (to which nsb_upload_density_grid / nsb_update_density_grid are
+    pinned). The threshold is min(NERF_MIN_OPTICAL_THICKNESS, mean): one case on each side of it."""
+    rng = np.random.default_rng(3)
+    G = 128 ** 3
+    grid = np.zeros(abi.NSB_GRID_CELLS, np.float32)
+    if fill == "sparse":   # mean < 0.01: the mean is the threshold
+        idx = rng.choice(3 * G, 200_000, replace=False)
+        grid[idx] = rng.uniform(0.0, 0.5, idx.size).astype(np.float32)
+        grid[rng.choice(3 * G, 5000, replace=False)] = -1.0
+    else:                  # mean > 0.01: NERF_MIN_OPTICAL_THICKNESS is
+        grid[: 3 * G] = rng.uniform(0.0, 0.06, 3 * G).astype(np.float32)
+    bits_o, mean_o = orc.density_grid_to_bitfield(grid)
+    bits_r = ref.grid_to_bitfield(grid, mean_o)
+    exact_mean = float(np.maximum(grid[:G].astype(np.float64), 0).sum() / G)  # the reference reduces the first cascade only (n_elements = 128^3)
+    print(f"\n{fill}: mean {mean_o:.6g} (float64 sum {exact_mean:.6g}); bitfield bytes differing {np.count_nonzero(bits_o != bits_r)}; set bits {np.unpackbits(bits_o).sum()}")
+    assert abs(mean_o - exact_mean) <= 1e-6 * max(exact_mean, 1e-6) + 1e-9
+    assert (mean_o < 0.01) == (fill == "sparse")
+    assert np.array_equal(bits_o, bits_r)
+    assert np.unpackbits(bits_o).sum() > 100_000
