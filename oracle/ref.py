@@ -167,6 +167,27 @@ def grid_to_bitfield(grid, mean: float):
     return bits
 
 
+def update_density_grid(params: "abi.NsbGridUpdate", grid, density, ops=None):
+    """Testbed::update_density_grid_nerf_operator + update_density_grid_mean_and_bitfield of the reference (testbed_nerf.cu:3533-3658).
+    density(positions [n, 3] float32, warped) -> [16, n] uint16 (fp16 bits, row 0 = raw density) is NerfNetwork::density.
+    Returns (grid, bitfield, mean)."""
+    grid = f32(grid).reshape(-1).copy()
+    bits = np.zeros(abi.NSB_BITFIELD_BYTES, np.uint8)
+    mean = C.c_float()
+
+    def cb(_user, pos_p, n, out_p):
+        pos = np.ctypeslib.as_array(pos_p, shape=(n, 3))
+        np.ctypeslib.as_array(out_p, shape=(16, n))[:] = density(pos)
+
+    fn = INFER_FN(cb)
+    arr, n_ops = _ops_array(ops)
+    l = lib()
+    l.ref_update_density_grid.argtypes = [C.POINTER(abi.NsbGridUpdate), C.POINTER(abi.NsbEditOp), C.c_int, INFER_FN, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    rc = l.ref_update_density_grid(C.byref(params), arr, n_ops, fn, None, _p(grid), _p(bits), C.byref(mean))
+    assert rc == 0
+    return grid, bits, mean.value
+
+
 def march_trace(frame: abi.NsbFrame, bitfield, pixels, max_samples: int):
     pixels = u32(pixels)
     n = pixels.size

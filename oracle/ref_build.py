@@ -58,6 +58,12 @@ EXTRACTS = {
         ("fn", r"^__global__ void init_rays_with_payload_kernel_nerf\("),
         ("fn", r"^void Testbed::NerfTracer::init_rays_from_camera\("),
         ("fn", r"^__global__ void clear_empty_space\("),
+        # the occupancy update through the operators, CPU build only (ref_common.inl guards the members)
+        ("fn", r"^__global__ void splat_grid_samples_nerf_max_nearest_neighbor_already_activated\("),
+        ("fn", r"^__global__ void ema_grid_samples_nerf\("),
+        ("fn", r"^__global__ void activate_network_density\("),
+        ("fn", r"^void Testbed::update_density_grid_nerf_operator\("),
+        ("fn", r"^void Testbed::update_density_grid_mean_and_bitfield\("),
         ("fn", r"^uint32_t Testbed::NerfTracer::trace\("),
         ("fn", r"^void Testbed::NerfTracer::enlarge\("),
         ("fn", r"^void Testbed::render_nerf\("),

@@ -7,6 +7,7 @@
 // declarations the cut-out members need (names = the reference's; only what the render path touches)
 // ---------------------------------------------------------------------------------------------------------------------
 namespace tcnn {
+static size_t g_scratch_floor = 0;
 struct GPUMemoryArena {
 	struct Allocation { std::vector<std::shared_ptr<void>> blocks; };
 };
@@ -15,13 +16,28 @@ template <typename... Types, size_t... I> std::tuple<Types*...> distribute_impl(
 	alloc->blocks.clear();
 	for (size_t k = 0; k < sizeof...(Types); ++k) alloc->blocks.push_back(nullptr);
 	const size_t elem[] = {sizeof(Types)...};
-	for (size_t k = 0; k < sizeof...(Types); ++k) alloc->blocks[k] = nsb_ref_alloc(sizes[k] * elem[k] + 64);
+	// g_scratch_floor: the reference's occupancy update launches compute_poisson_residual_density over 5*128^3 elements although its buffers hold
+	// n_density_grid_samples (testbed_nerf.cu:3612-3620): on the GPU those are stray reads/writes inside the arena that touch no used value; the CPU
+	// build gives them room instead of a segmentation fault.
+	for (size_t k = 0; k < sizeof...(Types); ++k) alloc->blocks[k] = nsb_ref_alloc(std::max(sizes[k] * elem[k], g_scratch_floor) + 64);
 	return std::tuple<Types*...>{(Types*)alloc->blocks[I].get()...};
 }
 template <typename... Types, typename... Sizes> std::tuple<Types*...> allocate_workspace_and_distribute(cudaStream_t, GPUMemoryArena::Allocation* alloc, Sizes... sizes) {
 	static_assert(sizeof...(Types) == sizeof...(Sizes), "one size per type");
 	const size_t s[] = {(size_t)sizes...};
 	return distribute_impl<Types...>(alloc, s, std::index_sequence_for<Types...>{});
+}
+// tcnn::reduce_sum(in, f, out, n, stream): *out += sum f(in[i]) — the device reduction's order is tcnn's own; here one double accumulator
+inline size_t reduce_sum_workspace_size(uint32_t) { return 1; }
+template <typename T, typename F> void reduce_sum(const T* in, F f, float* out, uint32_t n, cudaStream_t) {
+#if defined(__CUDACC__)
+	(void)in; (void)f; (void)out; (void)n;
+	throw std::runtime_error("reduce_sum: the occupancy update is pinned on the CPU build only");
+#else
+	double acc = 0.0;
+	for (uint32_t i = 0; i < n; ++i) acc += (double)f(in[i]);
+	*out += (float)acc;
+#endif
 }
 }  // namespace tcnn
 
@@ -42,9 +58,18 @@ typedef int (*ref_inference_fn)(void* user, const float* coords_dev, uint32_t n,
 #else
 typedef void (*ref_inference_fn)(void* user, const float* coords /*7 x n, column-major*/, uint32_t n, uint16_t* out /*16 x n row-major fp16*/);
 #endif
+typedef void (*ref_density_fn)(void* user, const float* positions /*3 x n, column-major, warped*/, uint32_t n, uint16_t* out /*16 x n row-major fp16, row 0 = raw density*/);
 template <typename T> struct NerfNetwork {
 	ref_inference_fn fn = nullptr;
+	ref_density_fn dfn = nullptr;  // NerfNetwork::density (nerf_network.h): the occupancy update's call (testbed_nerf.cu:3601-3603)
 	void* user = nullptr;
+	uint32_t padded_density_output_width() const { return 16; }
+	void density(cudaStream_t, const GPUMatrixDynamic<float>& input, GPUMatrixDynamic<T>& output, bool = true) {
+		if (!dfn) throw std::runtime_error("NerfNetwork::density call-back not set");
+		dfn(user, input.data(), input.n(), (uint16_t*)output.data());
+		n_inferred += input.n();
+		++n_calls;
+	}
 	uint64_t n_inferred = 0;
 	uint32_t n_calls = 0;
 	uint32_t padded_output_width() const { return 16; }
@@ -129,6 +154,11 @@ struct Testbed {
 		bool render_with_camera_distortion = false;  // testbed.h:648
 		CameraDistortion render_distortion;
 		tcnn::GPUMemory<uint8_t> density_grid_bitfield;
+		// the occupancy update (testbed.h:620-640)
+		tcnn::GPUMemory<float> density_grid, density_grid_mean;
+		uint32_t density_grid_ema_step = 0;
+		uint32_t max_cascade = 0;
+		uint8_t* get_density_grid_bitfield_mip(uint32_t mip) { return density_grid_bitfield.data() + grid_mip_offset(mip) / 8; }
 		int show_accel = -1;
 		float cone_angle_constant = 1.f / 256.f;
 		struct Training {
@@ -136,6 +166,7 @@ struct Testbed {
 			uint32_t n_images_for_training = 0;
 			tcnn::GPUMemory<TrainingXForm> transforms;
 			bool linear_colors = false;
+			float density_grid_decay = 0.95f;
 		} training;
 		ENerfActivation rgb_activation = ENerfActivation::Logistic;
 		ENerfActivation density_activation = ENerfActivation::Exponential;
@@ -158,6 +189,12 @@ struct Testbed {
 	void render_nerf(NerfNetwork<network_precision_t>& network, CudaRenderBuffer& render_buffer, const Vector2i& max_res, const Vector2f& focal_length,
 	                 const Matrix<float, 3, 4>& camera_matrix0, const Matrix<float, 3, 4>& camera_matrix1, const Vector4f& rolling_shutter, const Vector2f& screen_center,
 	                 bool apply_operators, cudaStream_t stream);
+	// the occupancy update through the operators (testbed_nerf.cu:3533-3658)
+	std::shared_ptr<NerfNetwork<network_precision_t>> m_nerf_network;
+	tcnn::default_rng_t m_rng;
+	cudaStream_t m_inference_stream = nullptr;
+	void update_density_grid_nerf_operator(uint32_t n_uniform_density_grid_samples, uint32_t n_nonuniform_density_grid_samples, bool reset_grid, cudaStream_t stream);
+	void update_density_grid_mean_and_bitfield(cudaStream_t stream);
 };
 
 // NsbFrame (ABI 3) -> the Testbed members render_nerf reads for the general camera, glow, environment and distortion maps
@@ -204,7 +241,6 @@ struct RefOpBase : EditOperator {
 	bool visualize_edit_gui(const Matrix<float, 4, 4>&, const Matrix<float, 4, 4>&, const Matrix<float, 4, 4>&, const Vector2f&, float, float) override { return false; }
 	void draw_gl(const Vector2i&, const Vector2f&, const Matrix<float, 3, 4>&, const Vector2f&) override {}
 	bool handle_keyboard() override { return false; }
-	void map_positions(cudaStream_t, tcnn::PitchedPtr<NerfPosition>, tcnn::GPUMatrixDynamic<bool>&, uint32_t) const override {}
 	nlohmann::json to_json() override { return {}; }
 };
 
@@ -216,6 +252,20 @@ struct RefCageOp : RefOpBase {
 		tcnn::linear_kernel(interpolate_tet, 0, stream, n_elements, nerf_coords, empty_mask.data(), (bool)op.copy, bb(op.scene_aabb_min, op.scene_aabb_max),
 		                    bb(op.warped_bbox_min, op.warped_bbox_max), bb(op.original_warped_bbox_min, op.original_warped_bbox_max), op.tet_lut_idx, op.tet_lut_offsets, op.tets,
 		                    (const Vector3f*)op.vertices, (const Vector3f*)op.original_vertices, (const Matrix3f*)op.local_rotations, op.original_bitfield);
+	}
+	// CageDeformation::map_positions (cage_deformation.cu:624-645) and ::compute_poisson_residual_density (:647-672); no cutting plane (m_plane_dir = 0)
+	void map_positions(cudaStream_t stream, tcnn::PitchedPtr<NerfPosition> nerf_pos, tcnn::GPUMatrixDynamic<bool>& empty_mask, uint32_t n_elements) const override {
+		if (op.n_tets == 0) return;
+		tcnn::linear_kernel(interpolate_tet_pos, 0, stream, n_elements, nerf_pos, empty_mask.data(), bb(op.scene_aabb_min, op.scene_aabb_max), bb(op.warped_bbox_min, op.warped_bbox_max),
+		                    bb(op.original_warped_bbox_min, op.original_warped_bbox_max), op.tet_lut_idx, op.tet_lut_offsets, op.tets, (const Vector3f*)op.vertices,
+		                    (const Vector3f*)op.original_vertices, op.original_bitfield);
+	}
+	void compute_poisson_residual_density(cudaStream_t stream, const uint32_t n_elements, tcnn::PitchedPtr<NerfPosition> input_position,
+	                                      tcnn::network_precision_t* density_network_output) const override {
+		if (!op.apply_poisson || op.n_tets == 0 || !op.boundary_residual_density) return;
+		tcnn::linear_kernel(compute_poisson_residual_density_kernel, 0, stream, n_elements, input_position, density_network_output, bb(op.scene_aabb_min, op.scene_aabb_max),
+		                    Vector3f(Vector3f::Zero()), Vector3f(Vector3f::Zero()), bb(op.bbox_min, op.bbox_max), op.tet_lut_idx, op.tet_lut_offsets, op.tets,
+		                    (const Vector3f*)op.vertices, op.boundary_residual_density);
 	}
 	void compute_poisson_full_residuals(cudaStream_t stream, const uint32_t n_elements, NerfPayload* payloads, tcnn::PitchedPtr<NerfCoordinate> network_input,
 	                                    SH9RGB* __restrict__ sh_boundary, float* __restrict__ out_density_boundary, float* __restrict__ residual_density_boundary) const override {
@@ -245,6 +295,12 @@ struct RefAffineOp : RefOpBase {
 		tcnn::linear_kernel(translate_in_box, 0, stream, n_elements, nerf_coords, op.hide_original ? empty_mask.data() : (bool*)nullptr, abox(op.selection_box),
 		                    abox(op.destination_box), Vector3f(op.translation[0], op.translation[1], op.translation[2]), Vector3f(op.scale[0], op.scale[1], op.scale[2]), R,
 		                    (bool)op.correct_dir);
+	}
+	// AffineDuplication::map_positions (affine_duplication.cu:137-150)
+	void map_positions(cudaStream_t stream, tcnn::PitchedPtr<NerfPosition> nerf_pos, tcnn::GPUMatrixDynamic<bool>& empty_mask, uint32_t n_elements) const override {
+		Matrix3f R; memcpy(R.data(), op.rotation, 9 * sizeof(float));
+		tcnn::linear_kernel(translate_in_box_pos, 0, stream, n_elements, nerf_pos, op.hide_original ? empty_mask.data() : (bool*)nullptr, abox(op.selection_box), abox(op.destination_box),
+		                    Vector3f(op.translation[0], op.translation[1], op.translation[2]), Vector3f(op.scale[0], op.scale[1], op.scale[2]), R);
 	}
 };
 static std::shared_ptr<EditOperator> make_op(const NsbEditOp& o) {

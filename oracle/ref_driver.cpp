@@ -213,6 +213,36 @@ int ref_render(const NsbFrame* f, const uint8_t* bitfield, const NsbEditOp* ops,
 	}
 }
 
+// ---- Testbed::update_density_grid_nerf_operator + update_density_grid_mean_and_bitfield, the reference's own (testbed_nerf.cu:3533-3658) ----
+// grid: float[5*128^3] in/out (the running density grid), bits: uint8[5*128^3/8] out, mean_out: density_grid_mean. NerfNetwork::density is the call-back.
+int ref_update_density_grid(const NsbGridUpdate* u, const NsbEditOp* ops, int n_ops, ref_density_fn dfn, void* user, float* grid, uint8_t* bits, float* mean_out) {
+	try {
+		const uint32_t n_cells = NERF_GRIDSIZE() * NERF_GRIDSIZE() * NERF_GRIDSIZE() * NERF_CASCADES();
+		Testbed tb;
+		tb.m_aabb = bb(u->train_aabb_min, u->train_aabb_max);
+		tb.m_nerf.density_grid.resize(n_cells);
+		tb.m_nerf.density_grid.copy_from_host(grid, n_cells);
+		tb.m_nerf.density_grid_ema_step = u->ema_step;
+		tb.m_nerf.max_cascade = (uint32_t)u->n_cascades - 1;
+		tb.m_nerf.training.density_grid_decay = u->decay;
+		tb.m_nerf.density_activation = (ENerfActivation)u->density_activation;
+		tb.m_rng.state = u->rng_state; tb.m_rng.inc = u->rng_inc;
+		if (u->apply_operators) for (int i = 0; i < n_ops; ++i) tb.m_nerf.tracer.add_edit_operator(make_op(ops[i]));
+		tb.m_nerf_network = std::make_shared<NerfNetwork<network_precision_t>>();
+		tb.m_nerf_network->dfn = dfn; tb.m_nerf_network->user = user;
+		tcnn::g_scratch_floor = (size_t)n_cells * 12;  // see ref_common.inl: room for the reference's over-long compute_poisson_residual_density launch
+		tb.update_density_grid_nerf_operator(u->n_uniform_samples, u->n_nonuniform_samples, u->reset_grid != 0, nullptr);
+		tcnn::g_scratch_floor = 0;
+		tb.m_nerf.density_grid.copy_to_host(grid, n_cells);
+		tb.m_nerf.density_grid_bitfield.copy_to_host(bits, NSB_BITFIELD_BYTES);
+		if (mean_out) tb.m_nerf.density_grid_mean.copy_to_host(mean_out, 1);
+		return 0;
+	} catch (const std::exception& e) {
+		fprintf(stderr, "ref_update_density_grid: %s\n", e.what());
+		return 1;
+	}
+}
+
 // ---- EditOperator::map_rays / compute_poisson_full_residuals on a flat batch (reverse list order, testbed_nerf.cu:2868,2899) ----
 int ref_map_rays(const NsbEditOp* ops, int n_ops, float* coords /*7 per sample*/, uint8_t* empty_mask, uint32_t n) {
 	static_assert(sizeof(NerfCoordinate) == 7 * sizeof(float), "NerfCoordinate layout");

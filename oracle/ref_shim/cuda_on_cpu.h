@@ -84,6 +84,8 @@ inline float atomicAdd(float* p, float v) {
 	do { memcpy(&f, &old, 4); f += v; memcpy(&neu, &f, 4); } while (!__atomic_compare_exchange_n(ip, &old, neu, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
 	memcpy(&f, &old, 4); return f;
 }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED); while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return old; }
 
 // kernel<<<blocks, threads, shmem, stream>>>(args...) is rewritten by oracle/ref_build.py into nsb_launch(blocks, threads, kernel, args...)

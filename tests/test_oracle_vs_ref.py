@@ -347,3 +347,54 @@ def test_bitfield_from_density_grid_vs_reference_kernels(fill):
     assert (mean_o < 0.01) == (fill == "sparse")
     assert np.array_equal(bits_o, bits_r)
     assert np.unpackbits(bits_o).sum() > 100_000
+
+
+@pytest.mark.parametrize("edited", [False, True])
+def test_occupancy_update_vs_reference_update_density_grid_nerf_operator(scene, oracle, edited):
+    """Row (f)-2 end to end: the reference's OWN Testbed::update_density_grid_nerf_operator + update_density_grid_mean_and_bitfield
+    (testbed_nerf.cu:3533-3658: sample draw, map_positions through the operators in reverse order, NerfNetwork::density, activate_network_density,
+    compute_poisson_residual_density, max-splat, EMA merge, mean, grid_to_bitfield, max-pools) with the oracle's density network plugged in, against
+    the oracle's update_density_grid — two consecutive updates (reset, then merge on an advanced m_rng), with and without E3 + membrane + affine."""
+    from nerfshop_b200.rng import Pcg32
+
+    model, occ = scene
+    ops = None
+    o = oracle
+    if edited:
+        cages = e3(model)
+        ops = [c.to_op() for c in cages]
+        ops.append(editing.AffineDuplication((0.5, 0.5, 0.5), (0.12, 0.12, 0.12), (0.03, 0.0, -0.1), rotation=ROT, hide_original=True, correct_dir=True).to_op())
+        o = orc.Oracle(model.desc, model.params, occ, ops)
+    plain = oracle
+
+    def density(pos):  # NerfNetwork::density: direction-free, rows = the density network's 16 outputs
+        c = np.zeros((pos.shape[0], 7), np.float32)
+        c[:, :3] = pos
+        c[:, 4:] = 0.5
+        return plain.inference(c, density_only=True)
+
+    rng = Pcg32(99)
+    grid_o = grid_r = np.full(abi.NSB_GRID_CELLS, 0.25, np.float32)  # reset_grid must wipe this
+    for step, (n_uni, n_non, reset) in enumerate([(120_000, 0, True), (60_000, 40_000, False)]):
+        u = abi.NsbGridUpdate()
+        u.n_uniform_samples, u.n_nonuniform_samples, u.reset_grid, u.n_cascades = n_uni, n_non, int(reset), 3
+        u.decay, u.ema_step, u.rng_state, u.rng_inc = 0.95, step, rng.state, rng.inc
+        u.train_aabb_min[:] = tuple(model.aabb_min)
+        u.train_aabb_max[:] = tuple(model.aabb_max)
+        u.density_activation, u.apply_operators = abi.NSB_ACT_EXPONENTIAL, int(edited)
+        grid_o, bits_o, mean_o = o.update_density_grid(u, grid_o)
+        grid_r, bits_r, mean_r = ref.update_density_grid(u, grid_r, density, ops=ops)
+        rng.advance(); rng.advance()  # m_rng.advance() after each of the two sample-generation launches
+        touched = (grid_o > 0) | (grid_r > 0)
+        same = grid_o == grid_r
+        rel = np.abs(grid_o - grid_r)[touched] / np.maximum(grid_r[touched], 1e-12)
+        print(f"\n{'E3+affine' if edited else 'no operators'} step {step}: {touched.sum()} cells touched, {(~same).sum()} differ (max rel {rel.max() if rel.size else 0:.2e}); "
+              f"mean {mean_o:.6g} vs {mean_r:.6g}; bitfield bytes differing {np.count_nonzero(bits_o != bits_r)}")
+        assert touched.sum() > 50_000
+        assert np.array_equal(grid_o > 0, grid_r > 0), "same cells touched"
+        # positions may differ by an ulp where the operators map them (gcc vs nvcc contraction of the tet barycentrics, DESIGN.md section 3): the raw
+        # fp16 density of such a sample moves by a few fp16 ulps (1 ulp = 1e-3 relative) — a handful of cells in 10^5
+        # and a sample within an ulp of a tet face may be mapped by one build and not by the other: at most a few cells in 10^5 differ freely
+        assert (~same).sum() <= 1e-4 * touched.sum() + 2 and (rel > 1e-2).sum() <= 3
+        assert abs(mean_o - mean_r) <= 1e-6 * max(mean_r, 1e-6) + 1e-9
+        assert np.count_nonzero(bits_o != bits_r) <= 2
