@@ -188,6 +188,27 @@ def update_density_grid(params: "abi.NsbGridUpdate", grid, density, ops=None):
     return grid, bits, mean.value
 
 
+def accumulate(frame, acc, sample_count: float, color_space: int):
+    """accumulate_kernel (render_buffer.cu:217-252): returns the new accumulate buffer."""
+    frame, acc = f32(frame), f32(acc).copy()
+    H, W = frame.shape[:2]
+    l = lib()
+    l.ref_accumulate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+    assert l.ref_accumulate(W, H, _p(frame), _p(acc), float(sample_count), int(color_space)) == 0
+    return acc
+
+
+def tonemap(acc, exposure: float, background, color_space: int, output_color_space: int, curve: int, clamp_output: bool):
+    """tonemap_kernel (render_buffer.cu:471-501) and the two tonemap() device functions (:254-332)."""
+    acc, bg = f32(acc), f32(background)
+    H, W = acc.shape[:2]
+    out = np.zeros_like(acc)
+    l = lib()
+    l.ref_tonemap.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    assert l.ref_tonemap(W, H, float(exposure), _p(bg), _p(acc), int(color_space), int(output_color_space), int(curve), int(bool(clamp_output)), _p(out)) == 0
+    return out
+
+
 def march_trace(frame: abi.NsbFrame, bitfield, pixels, max_samples: int):
     pixels = u32(pixels)
     n = pixels.size

@@ -68,6 +68,13 @@ EXTRACTS = {
         ("fn", r"^void Testbed::NerfTracer::enlarge\("),
         ("fn", r"^void Testbed::render_nerf\("),
     ]),
+    # frame post-process: accumulate / tonemap
+    "render_buffer": ("src/render_buffer.cu", [
+        ("fn", r"^__global__ void accumulate_kernel\("),
+        ("fn", r"^__device__ Array3f tonemap\(Array3f x, ETonemapCurve curve\)"),
+        ("fn", r"^__device__ Array3f tonemap\(Array3f col, const Array3f& exposure"),
+        ("fn", r"^__global__ void tonemap_kernel\("),
+    ]),
     "cage_deformation": ("src/editing/cage_deformation.cu", [
         ("fn", r"^__global__ void interpolate_tet_pos\("),
         ("fn", r"^__global__ void interpolate_tet\("),

@@ -221,6 +221,11 @@ static inline CameraDistortion frame_camera_distortion(const NsbFrame* f) {
 
 // ---- the reference's code ---------------------------------------------------------------------------------------------
 #include "testbed_nerf.inc"
+#ifndef __CUDACC__  // frame post-process: CPU build only (the tonemap kernel writes a GL surface on the GPU; here only its `lopi` copy is kept)
+typedef unsigned long long cudaSurfaceObject_t;
+template <typename V> inline void surf2Dwrite(V, cudaSurfaceObject_t, size_t, uint32_t) {}
+#include "render_buffer.inc"
+#endif
 #include "cage_deformation.inc"
 #include "affine_duplication.inc"
 #include "selection_utils.inc"

@@ -243,6 +243,28 @@ int ref_update_density_grid(const NsbGridUpdate* u, const NsbEditOp* ops, int n_
 	}
 }
 
+// ---- accumulate_kernel / tonemap_kernel (render_buffer.cu:217-252, 254-332, 471-501), the reference's own ----
+// frame, acc, out: float4[W*H]; background: 4 floats (sRGB); enums = common.h's EColorSpace / ETonemapCurve
+int ref_accumulate(int W, int H, const float* frame, float* acc, float sample_count, int color_space) {
+#pragma omp parallel for schedule(static)
+	for (int y = 0; y < H; ++y)
+		for (int x = 0; x < W; ++x) {
+			blockDim = dim3(1, 1, 1); gridDim = dim3(W, H, 1); blockIdx = {(uint32_t)x, (uint32_t)y, 0}; threadIdx = {0, 0, 0};
+			accumulate_kernel(Vector2i(W, H), (Array4f*)frame, (Array4f*)acc, sample_count, (EColorSpace)color_space);
+		}
+	return 0;
+}
+int ref_tonemap(int W, int H, float exposure, const float* background, const float* acc, int color_space, int output_color_space, int curve, int clamp_output, float* out) {
+	const Array4f bg(background[0], background[1], background[2], background[3]);
+#pragma omp parallel for schedule(static)
+	for (int y = 0; y < H; ++y)
+		for (int x = 0; x < W; ++x) {
+			blockDim = dim3(1, 1, 1); gridDim = dim3(W, H, 1); blockIdx = {(uint32_t)x, (uint32_t)y, 0}; threadIdx = {0, 0, 0};
+			tonemap_kernel(Vector2i(W, H), exposure, bg, (Array4f*)acc, (EColorSpace)color_space, (EColorSpace)output_color_space, (ETonemapCurve)curve, clamp_output != 0, 0, (Vector4f*)out);
+		}
+	return 0;
+}
+
 // ---- EditOperator::map_rays / compute_poisson_full_residuals on a flat batch (reverse list order, testbed_nerf.cu:2868,2899) ----
 int ref_map_rays(const NsbEditOp* ops, int n_ops, float* coords /*7 per sample*/, uint8_t* empty_mask, uint32_t n) {
 	static_assert(sizeof(NerfCoordinate) == 7 * sizeof(float), "NerfCoordinate layout");

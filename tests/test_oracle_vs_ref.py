@@ -398,3 +398,34 @@ def test_occupancy_update_vs_reference_update_density_grid_nerf_operator(scene, 
         assert (~same).sum() <= 1e-4 * touched.sum() + 2 and (rel > 1e-2).sum() <= 3
         assert abs(mean_o - mean_r) <= 1e-6 * max(mean_r, 1e-6) + 1e-9
         assert np.count_nonzero(bits_o != bits_r) <= 2
+
+
+def test_accumulate_and_tonemap_vs_reference_kernels():
+    """Row (f)-4: accumulate_kernel and tonemap_kernel (render_buffer.cu:217-252, 254-332, 471-501), the reference's own, against the oracle's
+    accumulate / tonemap (to which nsb_accumulate / nsb_tonemap are pinned): every colour space, every curve, HDR and negative inputs."""
+    rng = np.random.default_rng(8)
+    H, W = 37, 53
+    frame = rng.uniform(-0.2, 3.0, (H, W, 4)).astype(np.float32)
+    frame[..., 3] = rng.uniform(0.0, 1.0, (H, W)).astype(np.float32)
+    worst_acc = worst_tm = 0.0
+    for cs in (abi.NSB_COLOR_LINEAR, abi.NSB_COLOR_SRGB, abi.NSB_COLOR_VISPOSNEG):
+        acc_o = acc_r = np.zeros_like(frame)
+        for spp in range(3):
+            fr = (frame * np.float32(1.0 + 0.1 * spp)).astype(np.float32)
+            acc_o = orc.accumulate(fr, acc_o, spp, cs)
+            acc_r = ref.accumulate(fr, acc_r, spp, cs)
+            worst_acc = max(worst_acc, float(np.abs(acc_o - acc_r).max()))
+            assert np.allclose(acc_o, acc_r, rtol=2e-6, atol=2e-7), (cs, spp)
+        for curve in (abi.NSB_TONEMAP_IDENTITY, abi.NSB_TONEMAP_ACES, abi.NSB_TONEMAP_HABLE, abi.NSB_TONEMAP_REINHARD):
+            for out_cs, clamp, exposure in ((abi.NSB_COLOR_SRGB, 1, 0.0), (abi.NSB_COLOR_LINEAR, 0, 0.7), (abi.NSB_COLOR_SRGB, 0, -1.3)):
+                p = abi.NsbTonemap()
+                p.color_space, p.output_color_space, p.tonemap_curve, p.clamp_output_color, p.exposure = cs, out_cs, curve, clamp, exposure
+                p.background_color[:] = (0.2, 0.4, 0.6, 0.8)
+                t_o = orc.tonemap(acc_o, p)
+                t_r = ref.tonemap(acc_r, exposure, list(p.background_color), cs, out_cs, curve, bool(clamp))
+                err = np.abs(t_o - t_r) / np.maximum(1.0, np.abs(t_r))
+                finite = np.isfinite(t_r)
+                assert np.array_equal(np.isfinite(t_o), finite)
+                worst_tm = max(worst_tm, float(err[finite].max()))
+                assert err[finite].max() < 2e-6, (cs, curve, out_cs, clamp, exposure, float(err[finite].max()))
+    print(f"\naccumulate max |diff| {worst_acc:.2e}; tonemap max relative diff {worst_tm:.2e}")
