@@ -6,14 +6,17 @@
  * cpu_baseline / --impl reference legs of bench.py do, and only as the checker /
  * CPU baseline.
  *
- * PARITY UNPINNED: the reference has no tests, golden vectors or fixtures for this
- * path, it cannot be compiled here (tiny-cuda-nn and Eigen are
- * absent submodules), and the hash-grid / SH / fully-fused-MLP arithmetic lives in
- * the un-vendored private fork gitlab.inria.fr/cjambon/tcnn-pyngp.git@pyngp-api
- * (commit unrecorded). Those three ops restate the published tiny-cuda-nn algorithm
- * of that era; everything else follows the in-tree reference
- * line by line as cited on each function. The golden vectors under tests/golden/
- * are minted by this file (tests/golden/make_golden.py).
+ * PARITY: pinned to the reference's own code for everything that lives in /root/reference. oracle/ref_build.py compiles
+ * the reference's sources for this path (Testbed::render_nerf, NerfTracer::trace / init_rays_from_camera, every kernel they
+ * launch, the edit-operator kernels, update_density_grid_nerf_operator, accumulate / tonemap, mvc.h, svd3.h, build_tet_grid)
+ * from where they lie into oracle/_ref/ (CPU build, and an nvcc build for the GPU tests) behind stand-ins for the absent
+ * submodules; tests/test_oracle_vs_ref.py and tests/test_frame_extras_cpu.py hold this file to them (identical sample
+ * streams, frames <= 6.5e-4, identical occupancy grids / bitfields / tet LUTs). The reference ships no tests, golden vectors or
+ * fixtures of its own (SURVEY.md sections 4, 8c) and its build system cannot run here (tiny-cuda-nn, Eigen, ... are absent
+ * submodules). STILL UNPINNED: the hash-grid / SH / fully-fused-MLP arithmetic, which lives in the un-vendored private fork
+ * gitlab.inria.fr/cjambon/tcnn-pyngp.git@pyngp-api (commit unrecorded): those three ops restate the published tiny-cuda-nn
+ * algorithm of that era with the accumulator rounding policy as an explicit switch (orc_set_mlp_policy).
+ * The golden vectors under tests/golden/ are minted by this file (tests/golden/make_golden.py).
  *
  * Numerics contract (shared with the CUDA path): fp32 ops exactly as
  * written here, one rounding per operator, FMA only where fmaf() is spelled out
