@@ -209,6 +209,18 @@ def tonemap(acc, exposure: float, background, color_space: int, output_color_spa
     return out
 
 
+def membrane_blend(gamma, inside_density, outside_density, inside_shs, outside_shs):
+    """The loop of GrowingSelection::interpolate_poisson_boundary (growing_selection.cu:2363-2392): (boundary_shs [nv, 27], outside_density, residual_density)."""
+    g = f32(gamma)
+    nv, ncv = g.shape
+    arrs = [f32(a) for a in (inside_density, outside_density, inside_shs, outside_shs)]
+    b_shs, b_od, b_rd = np.zeros((nv, 27), np.float32), np.zeros(nv, np.float32), np.zeros(nv, np.float32)
+    l = lib()
+    l.ref_membrane_blend.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 7
+    assert l.ref_membrane_blend(_p(g), nv, ncv, *[_p(a) for a in arrs], _p(b_shs), _p(b_od), _p(b_rd)) == 0
+    return b_shs, b_od, b_rd
+
+
 def march_trace(frame: abi.NsbFrame, bitfield, pixels, max_samples: int):
     pixels = u32(pixels)
     n = pixels.size

@@ -100,6 +100,11 @@ EXTRACTS = {
         ("fn", r"^void Cage<float_t, point_t>::compute_mvc\("),
         ("fn", r"^void Cage<float_t, point_t>::interpolate_with_mvc\(const std::vector<std::vector<float_t>>& weights"),
     ]),
+    # the membrane blend: the loop of GrowingSelection::interpolate_poisson_boundary, between the two
+    # compute_poisson_boundary calls above it (network evaluation, std::rand) and the uploads below it; ref_driver.cpp supplies the named objects
+    "growing_selection": ("src/editing/tools/growing_selection.cu", [
+        ("range", r"^\tuint32_t n_tet_vertices = tet_interpolation_mesh->vertices\.size\(\);", r"^\t\tboundary_residual_density_host\[i\] = std::max\(boundary_residual_density_host\[i\], 0\.f\);"),
+    ]),
     "selection_utils": ("src/editing/tools/selection_utils.cu", [
         ("fn", r"^Eigen::Vector3f get_cell_pos\("),
         ("fn", r"^Eigen::Vector3i get_cell_at_pos\("),
@@ -168,12 +173,26 @@ def cut(lines, kind, pattern):
                 break
             i += 1
         end = i
+    elif kind == "range":
+        # ("range", first-line anchor, last-line anchor): statements out of the middle of a member whose surroundings cannot be compiled here
+        raise RuntimeError("range cuts take two anchors: use cut_range")
     else:
         i = start
         while ";" not in lines[i]:
             i += 1
         end = i
     return first, end
+
+
+def cut_range(lines, first_pattern, last_pattern):
+    a, b = re.compile(first_pattern), re.compile(last_pattern)
+    starts = [i for i, l in enumerate(lines) if a.search(l)]
+    if len(starts) != 1:
+        raise RuntimeError(f"anchor {first_pattern!r}: {len(starts)} matches (expected exactly 1)")
+    ends = [i for i in range(starts[0], len(lines)) if b.search(lines[i])]
+    if not ends:
+        raise RuntimeError(f"anchor {last_pattern!r}: no match after line {starts[0] + 1}")
+    return starts[0], ends[0]
 
 
 def extract_all(gen_dir: str):
@@ -184,8 +203,9 @@ def extract_all(gen_dir: str):
         with open(path, "r", encoding="utf-8", errors="replace") as fh:
             lines = fh.read().split("\n")
         parts = []
-        for kind, pattern in items:
-            a, b = cut(lines, kind, pattern)
+        for item in items:
+            kind, pattern = item[0], item[1]
+            a, b = cut_range(lines, item[1], item[2]) if kind == "range" else cut(lines, kind, pattern)
             manifest.append(f"{rel}:{a + 1}-{b + 1}  {pattern}")
             # the one mechanical rewrite: CUDA's launch syntax is not C++ (same kernel, same arguments, same grid)
             body = [LAUNCH_RX.sub(r"nsb_launch(\2, \3, \1, ", l) for l in lines[a:b + 1]]

@@ -265,6 +265,38 @@ int ref_tonemap(int W, int H, float exposure, const float* background, const flo
 	return 0;
 }
 
+// ---- the membrane blend: the loop of GrowingSelection::interpolate_poisson_boundary (growing_selection.cu:2363-2392), cut out of the member ----
+// gamma: [n_tet_vertices][n_cage_vertices]; *_shs: 27 floats per cage vertex; outputs per tet vertex
+int ref_membrane_blend(const float* gamma, uint32_t n_tv, uint32_t n_cv, const float* inside_density, const float* outside_density, const float* inside_shs,
+                       const float* outside_shs, float* b_shs, float* b_od, float* b_rd) {
+	struct Resizable { void resize(size_t) {} };
+	struct Mesh {
+		std::vector<Eigen::Vector3f> vertices;
+		std::vector<std::vector<float>> gamma_coordinates;
+		Resizable boundary_shs_gpu, boundary_residual_density_gpu, boundary_outside_density_gpu;
+	} mesh, *tet_interpolation_mesh = &mesh;
+	struct ProxyCage {
+		std::vector<Eigen::Vector3f> vertices;
+		std::vector<float> inside_density, outside_density;
+		std::vector<SH9RGB> inside_shs, outside_shs;
+	} proxy_cage;
+	mesh.vertices.resize(n_tv);
+	mesh.gamma_coordinates.assign(n_tv, std::vector<float>(n_cv));
+	for (uint32_t i = 0; i < n_tv; ++i) for (uint32_t j = 0; j < n_cv; ++j) mesh.gamma_coordinates[i][j] = gamma[(size_t)i * n_cv + j];
+	proxy_cage.vertices.resize(n_cv);
+	proxy_cage.inside_density.assign(inside_density, inside_density + n_cv);
+	proxy_cage.outside_density.assign(outside_density, outside_density + n_cv);
+	proxy_cage.inside_shs.resize(n_cv); proxy_cage.outside_shs.resize(n_cv);
+	memcpy((void*)proxy_cage.inside_shs.data(), inside_shs, (size_t)n_cv * 27 * sizeof(float));
+	memcpy((void*)proxy_cage.outside_shs.data(), outside_shs, (size_t)n_cv * 27 * sizeof(float));
+#include "growing_selection.inc"
+	}  // closes the cut-out's `for (int i = 0; i < n_tet_vertices; i++) {`
+	memcpy(b_shs, boundary_shs_host.data(), (size_t)n_tv * 27 * sizeof(float));
+	memcpy(b_od, boundary_outside_density_host.data(), (size_t)n_tv * sizeof(float));
+	memcpy(b_rd, boundary_residual_density_host.data(), (size_t)n_tv * sizeof(float));
+	return 0;
+}
+
 // ---- EditOperator::map_rays / compute_poisson_full_residuals on a flat batch (reverse list order, testbed_nerf.cu:2868,2899) ----
 int ref_map_rays(const NsbEditOp* ops, int n_ops, float* coords /*7 per sample*/, uint8_t* empty_mask, uint32_t n) {
 	static_assert(sizeof(NerfCoordinate) == 7 * sizeof(float), "NerfCoordinate layout");

@@ -429,3 +429,24 @@ def test_accumulate_and_tonemap_vs_reference_kernels():
                 worst_tm = max(worst_tm, float(err[finite].max()))
                 assert err[finite].max() < 2e-6, (cs, curve, out_cs, clamp, exposure, float(err[finite].max()))
     print(f"\naccumulate max |diff| {worst_acc:.2e}; tonemap max relative diff {worst_tm:.2e}")
+
+
+def test_membrane_blend_vs_reference_loop():
+    """Row (f)-4: the gamma-weighted blend of GrowingSelection::interpolate_poisson_boundary (growing_selection.cu:2363-2392), the reference's own
+    statements, against the oracle's membrane_blend (to which nsb_cage_set_membrane's k_membrane_blend is pinned bit for bit)."""
+    rng = np.random.default_rng(21)
+    nv, ncv = 300, 26
+    gamma = rng.uniform(-0.05, 1.0, (nv, ncv)).astype(np.float32)
+    gamma /= gamma.sum(1, keepdims=True)  # mean-value-like coordinates: partition of unity, a few negative
+    din = rng.uniform(0.0, 40.0, ncv).astype(np.float32)
+    dout = rng.uniform(0.05, 60.0, ncv).astype(np.float32)
+    din[:3] = 0.0
+    shs_in = rng.normal(0, 0.5, (ncv, 27)).astype(np.float32)
+    shs_out = rng.normal(0, 0.5, (ncv, 27)).astype(np.float32)
+    got = orc.membrane_blend(gamma, din, dout, shs_in, shs_out)
+    want = ref.membrane_blend(gamma, din, dout, shs_in, shs_out)
+    for name, a, b in zip(("boundary_shs", "outside_density", "residual_density"), got, want):
+        d = np.abs(a - b)
+        print(f"\n{name}: identical {np.array_equal(a, b)}, max |diff| {d.max():.2e} (values up to {np.abs(b).max():.1f})")
+        assert np.allclose(a, b, rtol=3e-6, atol=1e-6), name
+    assert (want[2] >= 0).all() and np.abs(want[0]).max() > 0.01
