@@ -221,6 +221,23 @@ def membrane_blend(gamma, inside_density, outside_density, inside_shs, outside_s
     return b_shs, b_od, b_rd
 
 
+JSON_CAGE, JSON_TET_MESH, JSON_AFFINE_BOX, JSON_AFFINE_BOX_MEMBER = range(4)
+
+
+def json_roundtrip(kind: int, obj):
+    """obj (a Python JSON value) -> the reference's from_json into its own class (Cage / TetMesh / AffineBoundingBox) -> its to_json -> Python value."""
+    import json
+
+    text = json.dumps(obj).encode()
+    l = lib()
+    l.ref_json_roundtrip.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    cap = 4 * len(text) + (1 << 16)
+    buf = C.create_string_buffer(cap)
+    n = l.ref_json_roundtrip(kind, text, buf, cap)
+    assert 0 < n <= cap, n
+    return json.loads(buf.value.decode())
+
+
 def march_trace(frame: abi.NsbFrame, bitfield, pixels, max_samples: int):
     pixels = u32(pixels)
     n = pixels.size

@@ -75,6 +75,14 @@ EXTRACTS = {
         ("fn", r"^__device__ Array3f tonemap\(Array3f col, const Array3f& exposure"),
         ("fn", r"^__global__ void tonemap_kernel\("),
     ]),
+    # the edits I/O glue: Eigen <-> json and BoundingBox <-> json; included by the shadow json_binding.h
+    "json_binding": ("include/neural-graphics-primitives/json_binding.h", [
+        ("range", r"^namespace Eigen \{", r"^\}$"),
+        ("range", r"^NGP_NAMESPACE_BEGIN$", r"^NGP_NAMESPACE_BEGIN$"),
+        ("fn", r"^inline void to_json\(nlohmann::json& j, const BoundingBox& box\)"),
+        ("fn", r"^inline void from_json\(const nlohmann::json& j, BoundingBox& box\)"),
+        ("range", r"^NGP_NAMESPACE_END$", r"^NGP_NAMESPACE_END$"),
+    ]),
     "cage_deformation": ("src/editing/cage_deformation.cu", [
         ("fn", r"^__global__ void interpolate_tet_pos\("),
         ("fn", r"^__global__ void interpolate_tet\("),

@@ -360,6 +360,37 @@ int ref_tet_mesh_build(const float* original_vertices, const float* deformed_ver
 	for (int k = 0; k < 4; ++k) { bbox[3 * k] = v[k].x(); bbox[3 * k + 1] = v[k].y(); bbox[3 * k + 2] = v[k].z(); }
 	return (int)mesh.tet_lut_offsets.size() == (int)NSB_GRID_CELLS + 1 ? 0 : 3;
 }
+// ---- the edits file's objects through the reference's OWN serialisers (row (f)-3) -----------------------------------------------------------
+// kind 0: Cage (cage.h:100-144), 1: TetMesh (tet_mesh.h:137-174), 2: AffineBoundingBox (affine_bounding_box.cuh:116-142, free functions),
+// 3: AffineBoundingBox via its to_json() member (:103-114, what AffineDuplication::to_json stores). The JSON text is parsed, read with the
+// reference's from_json into its class, written back with its to_json, and returned as text (returns the length needed, or -1 on error).
+int ref_json_roundtrip(int kind, const char* text_in, char* text_out, int capacity) {
+	try {
+		const nlohmann::json in = nlohmann::json::parse(text_in);
+		nlohmann::json out;
+		if (kind == 0) {
+			Cage<float, Eigen::Vector3f> cage;
+			from_json(in, cage);
+			to_json(out, cage);
+		} else if (kind == 1) {
+			TetMesh<float, Eigen::Vector3f> mesh;
+			from_json(in, mesh);
+			to_json(out, mesh);
+		} else if (kind == 2 || kind == 3) {
+			AffineBoundingBox box;
+			from_json(in, box);
+			if (kind == 2) to_json(out, box); else out = box.to_json();
+		} else {
+			return -1;
+		}
+		const std::string s = out.dump();
+		if ((int)s.size() + 1 <= capacity) memcpy(text_out, s.c_str(), s.size() + 1);
+		return (int)s.size() + 1;
+	} catch (const std::exception& e) {
+		fprintf(stderr, "ref_json_roundtrip: %s\n", e.what());
+		return -1;
+	}
+}
 void ref_svd3(uint32_t n, const float* A /*9 per, column-major*/, float* R /*U * V^T, column-major*/) {
 	for (uint32_t i = 0; i < n; ++i) {
 		Eigen::Matrix3f a, U, S, V; memcpy(a.data(), A + 9 * (size_t)i, 9 * sizeof(float));

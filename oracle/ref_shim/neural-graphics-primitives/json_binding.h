@@ -1,8 +1,8 @@
-// Shadows the reference's json_binding.h (nlohmann glue for Eigen types): TEST INFRASTRUCTURE ONLY (oracle/_ref), inert.
+// Shadows the reference's json_binding.h: TEST INFRASTRUCTURE ONLY (oracle/_ref). The real header pulls in the dataset loader (absent
+// filesystem submodule); what the edits I/O needs from it — the Eigen <-> json glue (json_binding.h:27-75) and BoundingBox's (:79-87) — is cut
+// out of the real file at build time (oracle/ref_build.py, json_binding.inc) and included here, over oracle/ref_shim/json/json.hpp.
 #pragma once
 #include <json/json.hpp>
 #include <neural-graphics-primitives/common.h>
-NGP_NAMESPACE_BEGIN
-template <typename T> inline void to_json(nlohmann::json&, const T&) {}
-template <typename T> inline void from_json(const nlohmann::json&, T&) {}
-NGP_NAMESPACE_END
+#include <neural-graphics-primitives/bounding_box.cuh>
+#include "json_binding.inc"

@@ -450,3 +450,71 @@ def test_membrane_blend_vs_reference_loop():
         print(f"\n{name}: identical {np.array_equal(a, b)}, max |diff| {d.max():.2e} (values up to {np.abs(b).max():.1f})")
         assert np.allclose(a, b, rtol=3e-6, atol=1e-6), name
     assert (want[2] >= 0).all() and np.abs(want[0]).max() > 0.01
+
+
+def test_edits_file_objects_through_the_reference_serialisers(tmp_path, scene):
+    """Row (f)-3: what nerfshop_b200.edits_io writes for a cage operator (proxy cage with membrane values + interpolation tet mesh) and for an affine
+    box is READ by the reference's own from_json into its Cage / TetMesh / AffineBoundingBox classes (cage.h:123-144, tet_mesh.h:156-174,
+    affine_bounding_box.cuh:116-126 over json_binding.h:27-87) and WRITTEN back by its to_json: every key the reference reads is present, every array
+    survives with its shape convention (vectors as [x, y, z], SH9RGB as 9 rows of 3, index lists flat), and edits_io reads the reference's output back
+    into an identical operator."""
+    import json
+
+    from nerfshop_b200 import edits_io
+
+    model, _ = scene
+    cage = make_cage(model, (0.5, 0.62, 0.78), (0.17, 0.17, 0.17), n_lattice=3)
+    rng = np.random.default_rng(5)
+    nc = cage.cage_original.shape[0]
+    cage.cage_shs = {"inside_shs": rng.normal(0, .3, (nc, 27)).astype(np.float32), "outside_shs": rng.normal(0, .3, (nc, 27)).astype(np.float32),
+                     "inside_density": rng.uniform(0, 20, nc).astype(np.float32), "outside_density": rng.uniform(1, 30, nc).astype(np.float32)}
+    R = np.array([[0.8, -0.6, 0], [0.6, 0.8, 0], [0, 0, 1]], np.float32)
+    aff = edits_io.AffineDuplicationWorld(edits_io.AffineBox((0.9, 0.7, 0.5), (0.2, 0.3, 0.2), R), (0.15, 0.05, -0.1), model.aabb_min, model.aabb_max,
+                                          scale=(1.2, 1.0, 0.8), rotation=R, hide_original=True, correct_dir=True)
+    path = str(tmp_path / "edits.json")
+    edits_io.save_edits(path, [cage, aff])
+    j = json.load(open(path))
+    cj, aj = j["edit_operators"]
+
+    def same(a, b, what):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        assert a.shape == b.shape, (what, a.shape, b.shape)
+        assert np.array_equal(a.astype(np.float32), b.astype(np.float32)), what
+
+    # Cage: from_json reads all 15 keys with .at() — a missing or mis-shaped one throws inside the reference's code
+    cage_back = ref.json_roundtrip(ref.JSON_CAGE, cj["proxy_cage"])
+    assert list(cage_back) == ["vertices", "indices", "normals", "initial_normals", "labels", "original_vertices", "colors", "outside_colors", "initial_colors",
+                               "new_shs", "initial_shs", "inside_shs", "outside_shs", "inside_density", "outside_density"]  # cage.h:102-121, in that order
+    for k in cage_back:
+        same(cage_back[k], cj["proxy_cage"][k], f"proxy_cage.{k}")
+    assert np.asarray(cage_back["inside_shs"]).shape == (nc, 9, 3)
+    # TetMesh
+    mesh_back = ref.json_roundtrip(ref.JSON_TET_MESH, cj["interpolation_mesh"])
+    assert list(mesh_back) == ["bbox", "original_bbox", "warped_bbox", "original_warped_bbox", "vertices", "indices", "original_vertices", "mvc_coordinates",
+                               "gamma_coordinates", "tets", "labels", "colors", "all_indices"]  # tet_mesh.h:139-154
+    for k in mesh_back:
+        if k.endswith("bbox"):
+            same(mesh_back[k]["min"], cj["interpolation_mesh"][k]["min"], k)
+            same(mesh_back[k]["max"], cj["interpolation_mesh"][k]["max"], k)
+        else:
+            same(mesh_back[k], cj["interpolation_mesh"][k], f"interpolation_mesh.{k}")
+    # AffineBoundingBox, both of the reference's writers (free function and member)
+    for kind in (ref.JSON_AFFINE_BOX, ref.JSON_AFFINE_BOX_MEMBER):
+        box_back = ref.json_roundtrip(kind, aj["selection_box"])
+        assert set(box_back) == {"min", "max", "rot_matrix", "u", "v", "w", "center", "scale"}
+        for k in box_back:
+            same(box_back[k], aj["selection_box"][k], f"selection_box.{k}")
+    # and the other direction: the file rebuilt from the reference's output loads into an identical operator list
+    cj2 = dict(cj, proxy_cage=cage_back, interpolation_mesh=mesh_back)
+    aj2 = dict(aj, selection_box=ref.json_roundtrip(ref.JSON_AFFINE_BOX, aj["selection_box"]))
+    path2 = str(tmp_path / "edits_ref.json")
+    json.dump({"edit_operators": [cj2, aj2]}, open(path2, "w"))
+    ops1 = edits_io.load_edits(path, model.aabb_min, model.aabb_max)
+    ops2 = edits_io.load_edits(path2, model.aabb_min, model.aabb_max)
+    for o1, o2 in zip(ops1, ops2):
+        p1, k1 = o1.to_op()
+        p2, k2 = o2.to_op()
+        cut = abi.NsbEditOp.tet_lut_offsets.offset
+        assert bytes(p1)[:cut] == bytes(p2)[:cut] and bytes(p1)[abi.NsbEditOp.selection_box.offset:] == bytes(p2)[abi.NsbEditOp.selection_box.offset:]
+        for name in k1:
+            assert np.array_equal(k1[name], k2[name]), name
