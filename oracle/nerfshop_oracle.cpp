@@ -1370,7 +1370,8 @@ int orc_update_density_grid(const OrcScene* s, const NsbGridUpdate* u, float* gr
 
 // ---- GrowingSelection::compute_poisson_boundary (growing_selection.cu:2220-2348) on the host --------------------------------
 // std::rand() jitter replaced by pcg32(seed) (two draws per sample, u then v), as include/nerfshop_b200.h documents.
-int orc_poisson_boundary(const OrcScene* s, const float* points, uint32_t n_points, const NsbBoundarySampling* p, float* density_out, float* shs_out,
+// `uniforms` (optional, 2 per sample in (k, i, j) order): the jitter the reference draws with std::rand() (:2245-2246); NULL = seeded pcg32.
+int orc_poisson_boundary_ex(const OrcScene* s, const float* points, uint32_t n_points, const NsbBoundarySampling* p, const float* uniforms, float* density_out, float* shs_out,
                          float* coords_out /*optional n*w*w*7*/) {
 	Model m;
 	if (!model_init(m, &s->desc, s->params, s->n_params)) return 1;
@@ -1382,8 +1383,10 @@ int orc_poisson_boundary(const OrcScene* s, const float* points, uint32_t n_poin
 	for (uint32_t k = 0; k < n_points; ++k)                                                  // :2238-2260
 		for (uint32_t i = 0; i < w; ++i)
 			for (uint32_t j = 0; j < w; ++j) {
-				float u = ((float)i + rng.next_float()) / (float)p->hemisphere_width;
-				float v = ((float)j + rng.next_float()) / (float)p->hemisphere_width;
+				const size_t si = (size_t)n_sh * k + (size_t)i * w + j;
+				const float ju = uniforms ? uniforms[2 * si] : rng.next_float(), jv = uniforms ? uniforms[2 * si + 1] : rng.next_float();
+				float u = ((float)i + ju) / (float)p->hemisphere_width;
+				float v = ((float)j + jv) / (float)p->hemisphere_width;
 				float theta = (float)(2.f * M_PI * v);
 				float phi = acosf(2.f * u - 1.f);
 				float x = cosf(theta) * sinf(phi), y = sinf(theta) * sinf(phi), z = cosf(phi);
@@ -1435,6 +1438,10 @@ int orc_poisson_boundary(const OrcScene* s, const float* points, uint32_t n_poin
 		for (int q = 0; q < 27; ++q) shs_out[(size_t)k * 27 + q] = sh[q] * scale;                // :2341
 	}
 	return 0;
+}
+int orc_poisson_boundary(const OrcScene* s, const float* points, uint32_t n_points, const NsbBoundarySampling* p, float* density_out, float* shs_out,
+                         float* coords_out /*optional n*w*w*7*/) {
+	return orc_poisson_boundary_ex(s, points, n_points, p, nullptr, density_out, shs_out, coords_out);
 }
 // ---- GrowingSelection::interpolate_poisson_boundary (growing_selection.cu:2350-2398) --------------------------------------
 int orc_membrane_blend(const float* gamma, uint32_t n_vertices, uint32_t n_cv, const float* inside_density, const float* outside_density,

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         l.orc_pcg32_advance.restype = None
         l.orc_update_density_grid.argtypes = [C.POINTER(OrcScene), C.POINTER(abi.NsbGridUpdate), C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
         l.orc_poisson_boundary.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.POINTER(abi.NsbBoundarySampling), C.c_void_p, C.c_void_p, C.c_void_p]
+        l.orc_poisson_boundary_ex.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.POINTER(abi.NsbBoundarySampling), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.orc_membrane_blend.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 7
         l.orc_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         l.orc_tonemap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(abi.NsbTonemap)]
@@ -162,6 +163,17 @@ class Oracle:
         rc = self.lib.orc_update_density_grid(C.byref(self.scene), C.byref(params), _ptr(grid), _ptr(bits), C.byref(mean), None if samples is None else _ptr(samples))
         assert rc == 0
         return (grid, bits, mean.value, samples) if want_samples else (grid, bits, mean.value)
+
+    def poisson_boundary_with_jitter(self, points: np.ndarray, params: "abi.NsbBoundarySampling", uniforms: np.ndarray):
+        """compute_poisson_boundary with the jitter given (2 uniforms per sample, (vertex, i, j) order) instead of drawn from pcg32: (density, shs, coords)."""
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        n = pts.shape[0]
+        u = np.ascontiguousarray(uniforms, np.float32).reshape(-1)
+        assert u.size == 2 * n * params.sampling_width ** 2
+        dens, shs = np.zeros(n, np.float32), np.zeros((n, 27), np.float32)
+        coords = np.zeros((n * params.sampling_width ** 2, 7), np.float32)
+        assert self.lib.orc_poisson_boundary_ex(C.byref(self.scene), _ptr(pts), n, C.byref(params), _ptr(u), _ptr(dens), _ptr(shs), _ptr(coords)) == 0
+        return dens, shs, coords
 
     def poisson_boundary(self, points: np.ndarray, params: "abi.NsbBoundarySampling", want_coords: bool = False):
         """GrowingSelection::compute_poisson_boundary: (density [n], shs [n, 27][, coords])."""

@@ -238,6 +238,27 @@ def json_roundtrip(kind: int, obj):
     return json.loads(buf.value.decode())
 
 
+def poisson_boundary(points, params: "abi.NsbBoundarySampling", bitfield, infer):
+    """GrowingSelection::compute_poisson_boundary of the reference (its jitter is std::rand(): seed libc's generator first).
+    infer(coords [n, 7]) -> [16, n] uint16 is NerfNetwork::inference_mixed_precision. Returns (density [n], shs [n, 27], coords seen by the network)."""
+    pts = f32(points).reshape(-1, 3)
+    n = pts.shape[0]
+    bitfield = np.ascontiguousarray(bitfield, np.uint8)
+    dens, shs = np.zeros(n, np.float32), np.zeros((n, 27), np.float32)
+    seen = []
+
+    def cb(_user, coords_p, m, out_p):
+        coords = np.ctypeslib.as_array(coords_p, shape=(m, 7)).copy()
+        seen.append(coords)
+        np.ctypeslib.as_array(out_p, shape=(16, m))[:] = infer(coords)
+
+    fn = INFER_FN(cb)
+    l = lib()
+    l.ref_poisson_boundary.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.NsbBoundarySampling), C.c_void_p, INFER_FN, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert l.ref_poisson_boundary(_p(pts), n, C.byref(params), _p(bitfield), fn, None, _p(dens), _p(shs)) == 0
+    return dens, shs, np.concatenate(seen)
+
+
 def march_trace(frame: abi.NsbFrame, bitfield, pixels, max_samples: int):
     pixels = u32(pixels)
     n = pixels.size

@@ -113,6 +113,15 @@ EXTRACTS = {
     "growing_selection": ("src/editing/tools/growing_selection.cu", [
         ("range", r"^\tuint32_t n_tet_vertices = tet_interpolation_mesh->vertices\.size\(\);", r"^\t\tboundary_residual_density_host\[i\] = std::max\(boundary_residual_density_host\[i\], 0\.f\);"),
     ]),
+    # the membrane boundary values (row (f)-4): GrowingSelection::compute_poisson_boundary with its two kernels, and project_sh9
+    "growing_selection_boundary": ("src/editing/tools/growing_selection.cu", [
+        ("fn", r"^__global__ void activate_network_output\("),
+        ("fn", r"^__global__ void filter_empty\("),
+        ("fn", r"^void GrowingSelection::compute_poisson_boundary\("),
+    ]),
+    "sh_utils": ("src/editing/tools/sh_utils.cu", [
+        ("fn", r"^SH9RGB project_sh9\(const Eigen::Vector3f& dir, const Eigen::Vector3f& rgb"),
+    ]),
     "selection_utils": ("src/editing/tools/selection_utils.cu", [
         ("fn", r"^Eigen::Vector3f get_cell_pos\("),
         ("fn", r"^Eigen::Vector3i get_cell_at_pos\("),

@@ -79,7 +79,14 @@ template <typename T> struct NerfNetwork {
 #if defined(__CUDACC__)
 		if (fn(user, input.data(), input.n(), (uint16_t*)output.data(), output.n(), (void*)stream) != 0) throw std::runtime_error("inference call-back failed");
 #else
-		fn(user, input.data(), input.n(), (uint16_t*)output.data());
+		if (output.layout() == CM) {  // GrowingSelection::compute_poisson_boundary reads a column-major output (sample-major, 16 per sample)
+			std::vector<uint16_t> tmp((size_t)16 * input.n());
+			fn(user, input.data(), input.n(), tmp.data());
+			uint16_t* o = (uint16_t*)output.data();
+			for (uint32_t i = 0; i < input.n(); ++i) for (uint32_t r = 0; r < 16; ++r) o[(size_t)i * 16 + r] = tmp[(size_t)r * input.n() + i];
+		} else {
+			fn(user, input.data(), input.n(), (uint16_t*)output.data());
+		}
 #endif
 		n_inferred += input.n();
 		++n_calls;
@@ -225,6 +232,22 @@ static inline CameraDistortion frame_camera_distortion(const NsbFrame* f) {
 typedef unsigned long long cudaSurfaceObject_t;
 template <typename V> inline void surf2Dwrite(V, cudaSurfaceObject_t, size_t, uint32_t) {}
 #include "render_buffer.inc"
+// growing_selection.h's members that compute_poisson_boundary touches (growing_selection.cu:2220-2348), same names
+SH9RGB project_sh9(const Eigen::Vector3f& dir, const Eigen::Vector3f& rgb, const float domega = 1.0f);
+struct GrowingSelection {
+	using point_t = Eigen::Vector3f;
+	Cage<float, point_t> proxy_cage;
+	struct { uint32_t sh_sampling_width = 10; } m_poisson_editing;
+	uint32_t m_hemisphere_width = 10;
+	std::shared_ptr<NerfNetwork<network_precision_t>> m_nerf_network;
+	BoundingBox m_aabb;
+	cudaStream_t m_stream = nullptr;
+	ENerfActivation m_rgb_activation = ENerfActivation::Logistic, m_density_activation = ENerfActivation::Exponential;
+	tcnn::GPUMemory<uint8_t> m_density_grid_bitfield;
+	void compute_poisson_boundary(const bool is_inside);
+};
+#include "sh_utils.inc"
+#include "growing_selection_boundary.inc"
 #endif
 #include "cage_deformation.inc"
 #include "affine_duplication.inc"

@@ -297,6 +297,34 @@ int ref_membrane_blend(const float* gamma, uint32_t n_tv, uint32_t n_cv, const f
 	return 0;
 }
 
+// ---- GrowingSelection::compute_poisson_boundary, the reference's own (growing_selection.cu:2220-2348); its jitter comes from std::rand() ----
+// points: [n x 3] world units (proxy-cage vertices); density_out [n], shs_out [n x 27]. The network is the call-back; it sees the sample coordinates.
+int ref_poisson_boundary(const float* points, uint32_t n_points, const NsbBoundarySampling* p, const uint8_t* bitfield, ref_inference_fn fn, void* user, float* density_out, float* shs_out) {
+	try {
+		GrowingSelection gs;
+		std::vector<Eigen::Vector3f> pts(n_points);
+		for (uint32_t i = 0; i < n_points; ++i) pts[i] = Eigen::Vector3f(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+		gs.proxy_cage.vertices = pts;
+		gs.proxy_cage.original_vertices = pts;
+		gs.m_poisson_editing.sh_sampling_width = p->sampling_width;
+		gs.m_hemisphere_width = p->hemisphere_width;
+		gs.m_aabb = bb(p->train_aabb_min, p->train_aabb_max);
+		gs.m_rgb_activation = (ENerfActivation)p->rgb_activation;
+		gs.m_density_activation = (ENerfActivation)p->density_activation;
+		gs.m_density_grid_bitfield.copy_from_host(bitfield, NSB_BITFIELD_BYTES);
+		gs.m_nerf_network = std::make_shared<NerfNetwork<network_precision_t>>();
+		gs.m_nerf_network->fn = fn; gs.m_nerf_network->user = user;
+		gs.compute_poisson_boundary(p->is_inside != 0);
+		const std::vector<float>& d = p->is_inside ? gs.proxy_cage.inside_density : gs.proxy_cage.outside_density;
+		const std::vector<SH9RGB>& sh = p->is_inside ? gs.proxy_cage.inside_shs : gs.proxy_cage.outside_shs;
+		for (uint32_t i = 0; i < n_points; ++i) { density_out[i] = d[i]; memcpy(shs_out + 27 * (size_t)i, sh[i].data(), 27 * sizeof(float)); }
+		return 0;
+	} catch (const std::exception& e) {
+		fprintf(stderr, "ref_poisson_boundary: %s\n", e.what());
+		return 1;
+	}
+}
+
 // ---- EditOperator::map_rays / compute_poisson_full_residuals on a flat batch (reverse list order, testbed_nerf.cu:2868,2899) ----
 int ref_map_rays(const NsbEditOp* ops, int n_ops, float* coords /*7 per sample*/, uint8_t* empty_mask, uint32_t n) {
 	static_assert(sizeof(NerfCoordinate) == 7 * sizeof(float), "NerfCoordinate layout");

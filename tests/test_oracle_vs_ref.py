@@ -518,3 +518,40 @@ def test_edits_file_objects_through_the_reference_serialisers(tmp_path, scene):
         assert bytes(p1)[:cut] == bytes(p2)[:cut] and bytes(p1)[abi.NsbEditOp.selection_box.offset:] == bytes(p2)[abi.NsbEditOp.selection_box.offset:]
         for name in k1:
             assert np.array_equal(k1[name], k2[name]), name
+
+
+@pytest.mark.parametrize("is_inside", [0, 1])
+def test_membrane_boundary_values_vs_reference_compute_poisson_boundary(scene, oracle, is_inside):
+    """Row (f)-4: GrowingSelection::compute_poisson_boundary (growing_selection.cu:2220-2348), the reference's own — direction sampling on the
+    hemisphere grid, inference, activate_network_output, filter_empty (inside pass), density of each vertex's first sample, Monte-Carlo SH9 fit with
+    project_sh9 (sh_utils.cu:30-70) — with the oracle's network plugged in, against the oracle's poisson_boundary fed the SAME jitter: the reference
+    draws it with std::rand(), so libc's generator is seeded identically for both (the product draws from a seeded pcg32 instead, DESIGN.md section 7)."""
+    import ctypes
+
+    model, occ = scene
+    libc = ctypes.CDLL(None)
+    libc.rand.restype = ctypes.c_int
+    rng = np.random.default_rng(17)
+    n, w = 23, 6
+    pts = (rng.uniform(0.25, 0.75, (n, 3)) * (np.array(model.aabb_max) - np.array(model.aabb_min)) + np.array(model.aabb_min)).astype(np.float32)
+    p = abi.NsbBoundarySampling()
+    p.sampling_width, p.hemisphere_width, p.seed = w, 7, 0
+    p.train_aabb_min[:] = tuple(model.aabb_min)
+    p.train_aabb_max[:] = tuple(model.aabb_max)
+    p.rgb_activation, p.density_activation, p.is_inside = abi.NSB_ACT_LOGISTIC, abi.NSB_ACT_EXPONENTIAL, is_inside
+    libc.srand(4242)
+    uniforms = (np.array([libc.rand() for _ in range(2 * n * w * w)], np.float32) / np.float32(2147483647)).astype(np.float32)  # (float)std::rand() / RAND_MAX
+    d_o, sh_o, coords_o = oracle.poisson_boundary_with_jitter(pts, p, uniforms)
+    libc.srand(4242)
+    d_r, sh_r, coords_r = ref.poisson_boundary(pts, p, occ, lambda c: oracle.inference(c))
+    coords_r = coords_r[: n * w * w]  # the reference pads the batch to tcnn::batch_size_granularity
+    dpos = np.abs(coords_o[:, :3] - coords_r[:, :3]).max()
+    ddir = np.abs(coords_o[:, 4:] - coords_r[:, 4:]).max()
+    print(f"\nis_inside {is_inside}: sample positions max |diff| {dpos:.1e}, directions {ddir:.1e}; density identical {np.array_equal(d_o, d_r)} "
+          f"(max |diff| {np.abs(d_o - d_r).max():.2e}, {np.count_nonzero(d_r == 0)} filtered); SH max |diff| {np.abs(sh_o - sh_r).max():.2e} of {np.abs(sh_r).max():.2f}")
+    assert dpos == 0.0 and ddir < 3e-7  # cos/sin/acos: glibc float vs the reference's double intermediates (std::cos of a float promotes nothing; M_PI is double)
+    assert np.array_equal(d_o == 0, d_r == 0)
+    assert np.allclose(d_o, d_r, rtol=2e-3, atol=1e-6)   # a direction 1 ulp apart may move the raw fp16 density by an ulp
+    assert np.abs(sh_o - sh_r).max() < 2e-3 * max(1.0, float(np.abs(sh_r).max()))
+    if is_inside:
+        assert np.count_nonzero(d_r == 0) > 0
